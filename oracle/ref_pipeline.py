@@ -1,0 +1,161 @@
+"""The reference path itself, as far as it can run on this image.
+
+TEST INFRASTRUCTURE ONLY (checker + CPU baseline).  Never imported by the product path.
+
+* `ref_modules()`  -> the reference's OWN Cython (`sauvola`, `optimiser`), compiled unmodified from
+  /root/reference/cython/*.pyx by oracle/build_ref.py into oracle/_ref (travels to the GPU box).
+* `ref_decompose()` -> create_mrc_hocr_components (mrc.py:334-471) for hocr_word_data == [] with
+  the reference's compiled kernels, real Pillow (`convert('L')`, `thumbnail`) and real scipy
+  (`gaussian_filter`).  The ~40 lines of glue are restated here because /root/reference does not
+  exist on the GPU box; tests/golden/make_golden.py checks this glue against the *imported*
+  reference mrc.py inside the build container.  scikit-image's estimate_sigma is not installed:
+  sigma comes from the oracle restatement (parity unpinned) or is injected by the caller.
+* `load_reference_mrc()` -> imports /root/reference/internetarchivepdf/mrc.py unmodified with stub
+  `fitz` / `skimage` modules (container only; used to make golden fixtures).
+"""
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+from . import build_ref
+from . import oracle as orc
+
+_mods = None
+
+
+def ref_modules():
+    """(sauvola, optimiser) reference extension modules, or None if oracle/_ref is not built."""
+    global _mods
+    if _mods is None:
+        if not build_ref.have_ref() and not build_ref.build():
+            return None
+        out = []
+        for name in ('sauvola', 'optimiser'):
+            path = build_ref.ref_so_path(name)
+            loader = importlib.machinery.ExtensionFileLoader(name, path)
+            spec = importlib.util.spec_from_loader(name, loader, origin=path)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+            out.append(mod)
+        _mods = tuple(out)
+    return _mods
+
+
+def ref_threshold_image(img, dpi, k=0.34, window=None):
+    """mrc.py:58-87 on the reference's binarise_sauvola."""
+    sauvola, _ = ref_modules()
+    window_size = window if window is not None else orc.window_for_dpi(dpi)
+    h, w = img.shape
+    out_img = np.ndarray(img.shape, dtype=bool)
+    out_img = np.reshape(out_img, w * h)
+    in_img = np.reshape(np.ascontiguousarray(img), w * h)
+    sauvola.binarise_sauvola(in_img, out_img.view(np.uint8), w, h, window_size, window_size, k, 128)
+    return np.invert(np.reshape(out_img, (h, w)))
+
+
+def ref_decompose(image, dpi=None, bg_downsample=None, fg_downsample=None, denoise_mask=None,
+                  window=None, sigma_est=None, mask_only=False):
+    """image: uint8 ndarray (H,W) or (H,W,3).  Same return dict as oracle.decompose()."""
+    from PIL import Image
+    from scipy import ndimage
+    _, optimiser = ref_modules()
+    pil = Image.fromarray(image)
+    gray = pil if pil.mode == 'L' else pil.convert('L')                       # mrc.py:358-363
+    width_, height_ = pil.size
+    mask_arr = np.array(Image.new('1', pil.size))                             # mrc.py:367
+    grayimgf = np.array(gray, dtype=np.float32)                               # mrc.py:372
+    if sigma_est is None:
+        sigma_est = orc.estimate_noise(np.array(gray))                        # mrc.py:305 (unpinned)
+    imgf = grayimgf
+    if sigma_est > 1.0:                                                       # mrc.py:309-311
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            imgf = ndimage.gaussian_filter(imgf, sigma=sigma_est * 0.1)
+    mask_arr |= ref_threshold_image(imgf.astype(np.uint8), dpi, window=window)  # mrc.py:325-329
+    if denoise_mask != orc.DENOISE_NONE:
+        if denoise_mask == orc.DENOISE_FAST:
+            optimiser.fast_mask_denoise(mask_arr.view(np.uint8), width_, height_, 4, 2)   # mrc.py:388
+        else:
+            raise ValueError('Invalid denoise option:', denoise_mask)
+    res = dict(mask=mask_arr, sigma=sigma_est, errors=set())
+    if mask_only:
+        return res
+    image_arr = np.array(pil)
+    m8 = mask_arr.view(np.uint8)
+    opt = optimiser.optimise_gray2 if pil.mode == 'L' else optimiser.optimise_rgb2
+    fg = opt(m8, image_arr, width_, height_, 3)                               # mrc.py:412-415
+    if fg_downsample is not None:
+        im2 = Image.fromarray(fg)
+        w, h = im2.size
+        wd, hd = int(w / fg_downsample), int(h / fg_downsample)
+        if wd > 0 and hd > 0:
+            im2.thumbnail((wd, hd))
+            fg = np.array(im2)
+        else:
+            res['errors'].add('too-small-to-downsample')
+    mask_inv = mask_arr ^ np.ones(mask_arr.shape, dtype=bool)                 # mrc.py:439
+    bg = opt(mask_inv.view(np.uint8), image_arr, width_, height_, 10)         # mrc.py:446-449
+    if bg_downsample is not None:
+        im2 = Image.fromarray(bg)
+        w, h = im2.size
+        wd, hd = int(w / bg_downsample), int(h / bg_downsample)
+        if wd > 0 and hd > 0:
+            im2.thumbnail((wd, hd))
+            bg = np.array(im2)
+        else:
+            res['errors'].add('too-small-to-downsample')
+    res['fg'], res['bg'] = fg, bg
+    return res
+
+
+def load_reference_mrc(reference_dir='/root/reference'):
+    """Import the UNMODIFIED reference internetarchivepdf/mrc.py (container only).  Third-party
+    modules that are not installed are stubbed: fitz (only fitz.TOOLS.set_icc is touched at
+    import, mrc.py:39-41) and skimage, whose estimate_sigma is bound to the oracle restatement."""
+    mrc_path = os.path.join(reference_dir, 'internetarchivepdf', 'mrc.py')
+    if not os.path.exists(mrc_path):
+        return None
+    sauvola, optimiser = ref_modules()
+    saved = {k: sys.modules.get(k) for k in ('sauvola', 'optimiser', 'fitz', 'skimage', 'skimage.filters',
+                                             'skimage.restoration', 'internetarchivepdf',
+                                             'internetarchivepdf.jpeg2000', 'internetarchivepdf.const')}
+    sys.modules['sauvola'], sys.modules['optimiser'] = sauvola, optimiser
+    fitz = types.ModuleType('fitz')
+    fitz.TOOLS = types.SimpleNamespace(set_icc=lambda *_: None)
+    sys.modules['fitz'] = fitz
+    sk = types.ModuleType('skimage')
+    skf = types.ModuleType('skimage.filters')
+    skf.threshold_local = skf.threshold_otsu = None
+    skr = types.ModuleType('skimage.restoration')
+    skr.denoise_tv_bregman = None
+
+    def estimate_sigma(arr):
+        a = np.asarray(arr)
+        if a.dtype != np.float32 or np.any(a != np.floor(a)) or a.min() < 0 or a.max() > 255:
+            raise NotImplementedError('stub estimate_sigma: only uint8-valued float32 input')
+        return orc.estimate_sigma_full(np.ascontiguousarray(a).astype(np.uint8))
+
+    skr.estimate_sigma = estimate_sigma
+    sys.modules.update({'skimage': sk, 'skimage.filters': skf, 'skimage.restoration': skr})
+    pkg = types.ModuleType('internetarchivepdf')
+    pkg.__path__ = [os.path.join(reference_dir, 'internetarchivepdf')]
+    sys.modules['internetarchivepdf'] = pkg
+    try:
+        spec = importlib.util.spec_from_file_location('internetarchivepdf.mrc', mrc_path)
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spec.loader.exec_module(mod)
+        # scipy.ndimage.filters alias (mrc.py:311) still resolves on scipy 1.18 with a warning
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
