@@ -1,0 +1,91 @@
+"""ctypes binding of libb200mrc.so (include/b200mrc.h).
+
+There is NO fallback: if the CUDA library is missing or no CUDA device is present, every compute
+call raises.  The oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200mrc.so')
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_ALIGNMENT = 0, -1, -2, -3, -4
+SAUVOLA_OR_INTO, SAUVOLA_RAW_INVERTED = 1, 2
+DECOMPOSE_DENOISE_FAST, DECOMPOSE_MASK_ONLY, DECOMPOSE_NO_NOISE_EST = 1, 2, 4
+MAX_WINDOW, MAX_OPT_N = 255, 16
+
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+i64 = C.c_int64
+
+
+class DecomposeArgs(C.Structure):
+    _fields_ = [
+        ('img', vp), ('img_pitch', i64), ('img_page_stride', i64), ('channels', C.c_int),
+        ('width', C.c_int), ('height', C.c_int), ('n_pages', C.c_int),
+        ('window', C.c_int),
+        ('k', C.c_double), ('R', C.c_double),
+        ('flags', C.c_int),
+        ('sigma_in', vp), ('sigma_out', vp),
+        ('mask', vp), ('mask_pitch', i64), ('mask_page_stride', i64),
+        ('fg', vp), ('fg_pitch', i64), ('fg_page_stride', i64), ('fg_plan', vp),
+        ('bg', vp), ('bg_pitch', i64), ('bg_page_stride', i64), ('bg_plan', vp),
+        ('workspace', vp), ('workspace_bytes', C.c_size_t),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/b200mrc.h declares
+PROTOTYPES = {
+    'b200mrc_version': (C.c_int, []),
+    'b200mrc_error_string': (C.c_char_p, [C.c_int]),
+    'b200mrc_launch_count': (C.c_uint64, []),
+    'b200mrc_rgb2gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]),
+    'b200mrc_sauvola': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_double, C.c_double, C.c_int, vp]),
+    'b200mrc_noise_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'b200mrc_estimate_noise': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
+    'b200mrc_gray_blur': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    'b200mrc_denoise_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'b200mrc_denoise': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]),
+    'b200mrc_optimise_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'b200mrc_optimise': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, vp, i64, i64, C.c_int, vp, i64, i64, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]),
+    'b200mrc_thumbnail_plan_create': (vp, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                           C.POINTER(C.c_int)]),
+    'b200mrc_resample_plan_destroy': (None, [vp]),
+    'b200mrc_resample_plan_out_size': (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'b200mrc_resample_workspace_bytes': (C.c_size_t, [vp, C.c_int]),
+    'b200mrc_resample': (C.c_int, [vp, vp, i64, i64, vp, i64, i64, C.c_int, vp, C.c_size_t, vp]),
+    'b200mrc_channel_stats': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    'b200mrc_special_gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    'b200mrc_decompose_workspace_bytes': (C.c_size_t, [C.POINTER(DecomposeArgs)]),
+    'b200mrc_decompose': (C.c_int, [C.POINTER(DecomposeArgs), vp]),
+}
+
+_lib = None
+
+
+class B200MrcError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200MrcError('libb200mrc.so not built (%s); run `python -c "import __graft_entry__ as g; g.build()"` '
+                               'or `make -C archive-pdf-tools_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)          # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().b200mrc_error_string(status)
+        raise B200MrcError('%s failed (%d): %s' % (what or 'b200mrc call', status, msg.decode() if msg else '?'))

@@ -1,0 +1,187 @@
+// api.cu -- library bookkeeping and b200mrc_decompose: the whole of create_mrc_hocr_components
+// (internetarchivepdf/mrc.py:334-471, hocr_word_data == []) enqueued on one stream for a
+// device-resident batch of pages:
+//     gray (mrc.py:358-363) -> estimate_noise (:305) -> conditional Gaussian blur (:309-311)
+//     -> Sauvola (:325) -> fast_mask_denoise (:388)            => yield mask   (:399)
+//     -> optimise fg n=3 (:412-415) [-> thumbnail (:420-434)]  => yield fg     (:436)
+//     -> optimise bg n=10 (:446-449) [-> thumbnail (:454-468)] => yield bg     (:470)
+// Nothing here synchronises with the host; per-page decisions (blur or not, radius) are taken
+// on the device from the sigma array.
+#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+
+struct b200mrc_resample_plan;
+
+namespace b200mrc {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+const DevInfo &dev_info()
+{
+    static DevInfo info[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!have[dev]) {
+        cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&info[dev].max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        have[dev] = true;
+    }
+    return info[dev];
+}
+
+// implemented in the kernel translation units
+size_t noise_workspace_bytes(int W, int H, int N);
+int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C, int W, int H, int N,
+                          double *sigma_out, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C,
+                     uint8_t *out, int64_t out_pitch, int64_t out_stride,
+                     int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st);
+size_t denoise_workspace_bytes(int W, int H, int N);
+int launch_denoise(uint8_t *mask, int64_t pitch, int64_t stride, int W, int H, int N,
+                   void *workspace, size_t workspace_bytes, cudaStream_t st);
+size_t optimise_workspace_bytes(int W, int H, int N);
+int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
+                    const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                    uint8_t *ofg, int64_t fpitch, int64_t fstride, int nfg,
+                    uint8_t *obg, int64_t bpitch, int64_t bstride, int nbg,
+                    int W, int H, int N, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+namespace {
+
+struct DecomposeLayout {
+    size_t gray_pitch, gray_page;
+    size_t full_pitch, full_page;          // full-resolution fg / bg planes when downsampled
+    size_t off_sigma, off_gray, off_fgfull, off_bgfull, off_scratch, scratch_bytes, total;
+};
+
+DecomposeLayout decompose_layout(const b200mrc_decompose_args *a)
+{
+    DecomposeLayout L;
+    memset(&L, 0, sizeof(L));
+    const int W = a->width, H = a->height, N = a->n_pages, C = a->channels;
+    const bool mask_only = (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) != 0;
+    L.gray_pitch = align_up((size_t)W, 16); L.gray_page = L.gray_pitch * H;
+    L.full_pitch = align_up((size_t)W * C, 16); L.full_page = L.full_pitch * H;
+    Carver c(nullptr, 0);
+    L.off_sigma = (size_t)((uint8_t *)c.take<double>(N) - (uint8_t *)nullptr);
+    L.off_gray = (size_t)((uint8_t *)c.take<uint8_t>(L.gray_page * N) - (uint8_t *)nullptr);
+    if (!mask_only && a->fg_plan) L.off_fgfull = (size_t)((uint8_t *)c.take<uint8_t>(L.full_page * N) - (uint8_t *)nullptr);
+    if (!mask_only && a->bg_plan) L.off_bgfull = (size_t)((uint8_t *)c.take<uint8_t>(L.full_page * N) - (uint8_t *)nullptr);
+    // stages run one after another on the stream: they share one scratch region
+    size_t s = noise_workspace_bytes(W, H, N);
+    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) s = std::max(s, denoise_workspace_bytes(W, H, N));
+    if (!mask_only) {
+        s = std::max(s, optimise_workspace_bytes(W, H, N));
+        if (a->fg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->fg_plan, N));
+        if (a->bg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->bg_plan, N));
+    }
+    L.scratch_bytes = s;
+    L.off_scratch = (size_t)((uint8_t *)c.take<uint8_t>(s) - (uint8_t *)nullptr);
+    L.total = c.used();
+    return L;
+}
+
+int check_args(const b200mrc_decompose_args *a)
+{
+    if (!a || !a->img || !a->mask) return B200MRC_ERR_INVALID;
+    if (a->width <= 0 || a->height <= 0 || a->n_pages <= 0) return B200MRC_ERR_INVALID;
+    if (a->channels != 1 && a->channels != 3) return B200MRC_ERR_UNSUPPORTED;
+    if (a->n_pages > 65535) return B200MRC_ERR_UNSUPPORTED;
+    if (a->window < 1 || a->window > B200MRC_MAX_WINDOW) return B200MRC_ERR_UNSUPPORTED;
+    if (!(a->flags & B200MRC_DECOMPOSE_MASK_ONLY) && (!a->fg || !a->bg)) return B200MRC_ERR_INVALID;
+    if ((a->mask_pitch & 3) || ((uintptr_t)a->mask & 3) || (a->mask_page_stride & 3) || a->mask_pitch < a->width)
+        return B200MRC_ERR_ALIGNMENT;
+    return B200MRC_OK;
+}
+
+}  // namespace
+}  // namespace b200mrc
+
+using namespace b200mrc;
+
+extern "C" int b200mrc_version(void) { return B200MRC_VERSION; }
+
+extern "C" uint64_t b200mrc_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" const char *b200mrc_error_string(int status)
+{
+    switch (status) {
+    case B200MRC_OK: return "ok";
+    case B200MRC_ERR_INVALID: return "b200mrc: invalid argument";
+    case B200MRC_ERR_UNSUPPORTED: return "b200mrc: parameter outside the implemented range";
+    case B200MRC_ERR_WORKSPACE: return "b200mrc: workspace too small";
+    case B200MRC_ERR_ALIGNMENT: return "b200mrc: pointer/pitch alignment requirement violated";
+    default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "b200mrc: unknown error";
+}
+
+extern "C" size_t b200mrc_decompose_workspace_bytes(const b200mrc_decompose_args *a)
+{
+    if (check_args(a) != B200MRC_OK) return 0;
+    return decompose_layout(a).total;
+}
+
+extern "C" int b200mrc_decompose(const b200mrc_decompose_args *a, void *stream)
+{
+    int rc = check_args(a);
+    if (rc != B200MRC_OK) return rc;
+    const DecomposeLayout L = decompose_layout(a);
+    if (!a->workspace || a->workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)a->workspace;
+    const int W = a->width, H = a->height, N = a->n_pages, C = a->channels;
+    double *sigma = (double *)(ws + L.off_sigma);
+    uint8_t *gray = ws + L.off_gray;
+    void *scratch = ws + L.off_scratch;
+
+    // ---- noise estimate (or injected sigma)
+    const double *sigma_used = sigma;
+    if (a->flags & B200MRC_DECOMPOSE_NO_NOISE_EST) {
+        if (a->sigma_in) B200MRC_CUDA_TRY(cudaMemcpyAsync(sigma, a->sigma_in, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+        else sigma_used = nullptr;
+    } else {
+        rc = launch_estimate_noise(a->img, a->img_pitch, a->img_page_stride, C, W, H, N, sigma, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->sigma_out) {
+        if (sigma_used) B200MRC_CUDA_TRY(cudaMemcpyAsync(a->sigma_out, sigma, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+        else B200MRC_CUDA_TRY(cudaMemsetAsync(a->sigma_out, 0, sizeof(double) * N, st));
+    }
+    // ---- gray (+ blur where sigma > 1)
+    rc = launch_gray_blur(a->img, a->img_pitch, a->img_page_stride, C, gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page,
+                          W, H, N, sigma_used, nullptr, st);
+    if (rc) return rc;
+    // ---- Sauvola: mask = threshold_image(gray)   (the hOCR mask is empty: OR is a plain store)
+    rc = b200mrc_sauvola(gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page, a->mask, a->mask_pitch, a->mask_page_stride,
+                         W, H, N, a->window, a->window, a->k, a->R, 0, st);
+    if (rc) return rc;
+    // ---- denoise
+    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) {
+        rc = launch_denoise(a->mask, a->mask_pitch, a->mask_page_stride, W, H, N, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) return B200MRC_OK;
+
+    // ---- fg / bg
+    uint8_t *fg_full = a->fg_plan ? ws + L.off_fgfull : a->fg;
+    uint8_t *bg_full = a->bg_plan ? ws + L.off_bgfull : a->bg;
+    const int64_t fgp = a->fg_plan ? (int64_t)L.full_pitch : a->fg_pitch, fgs = a->fg_plan ? (int64_t)L.full_page : a->fg_page_stride;
+    const int64_t bgp = a->bg_plan ? (int64_t)L.full_pitch : a->bg_pitch, bgs = a->bg_plan ? (int64_t)L.full_page : a->bg_page_stride;
+    rc = launch_optimise(a->mask, a->mask_pitch, a->mask_page_stride, a->img, a->img_pitch, a->img_page_stride, C,
+                         fg_full, fgp, fgs, 3, bg_full, bgp, bgs, 10, W, H, N, scratch, L.scratch_bytes, st);
+    if (rc) return rc;
+    if (a->fg_plan) {
+        rc = b200mrc_resample(a->fg_plan, fg_full, fgp, fgs, a->fg, a->fg_pitch, a->fg_page_stride, N, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->bg_plan) {
+        rc = b200mrc_resample(a->bg_plan, bg_full, bgp, bgs, a->bg, a->bg_pitch, a->bg_page_stride, N, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    return B200MRC_OK;
+}

@@ -1,0 +1,208 @@
+// gray_blur.cu -- k_gray_blur: PIL convert('L') (mrc.py:358-363) fused with the conditional
+// Gaussian pre-blur of create_threshold_mask (mrc.py:305-325):
+//     if sigma_est > 1.0: imgf = scipy.ndimage.gaussian_filter(imgf, sigma=sigma_est*0.1)
+//     ... imgf.astype(np.uint8)
+// scipy semantics restated (see oracle/mrc_oracle.c orc_gauss_blur, pinned bit-exact against
+// scipy 1.18): radius = int(4*sigma+0.5); weights exp(-0.5/sigma^2 * j^2) / sum in double;
+// correlate1d axis 0 then axis 1, symmetric fast path acc = x*w0; for j=radius..1:
+// acc += (x[i-j] + x[i+j]) * w_j in double (no FMA), float32 store after each axis; 'reflect'.
+//
+// One CTA = one output tile of one page: gray tile + halo -> smem (u8), vertical pass -> smem
+// (f32), horizontal pass -> uint8 truncation -> global.  sigma lives on the device, so the
+// per-page decision (blur or plain gray copy, and the radius) is taken by the kernel without a
+// host round trip; two tile configurations cover radius 0..16 and 17..128.
+#include "common.cuh"
+
+namespace b200mrc {
+namespace {
+
+struct GrayBlurParams {
+    const uint8_t *in; int64_t in_pitch, in_stride; int C;
+    uint8_t *out; int64_t out_pitch, out_stride;
+    int W, H;
+    const double *sigma;     // device, per page, may be null
+    int *err;                // device error flag (radius out of range), may be null
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (n == 1) return 0;
+    const int per = 2 * n;
+    i %= per; if (i < 0) i += per;
+    return i < n ? i : per - 1 - i;
+}
+
+__device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch, int C, int y, int x)
+{
+    const uint8_t *px = page + (int64_t)y * pitch + (int64_t)x * C;
+    if (C == 1) return px[0];
+    return luma_l24(px[0], px[1], px[2]);
+}
+
+// numpy pairwise sum (n <= 128 path): what phi_x.sum() does in scipy's _gaussian_kernel1d
+__device__ double np_sum(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; i++) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+template <int RLO, int RHI, int TH, int TW>
+__global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
+{
+    constexpr int GW = TW + 2 * RHI;           // smem row length (u8 tile and f32 tile)
+    constexpr int GH = TH + 2 * RHI;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    double *sw = reinterpret_cast<double *>(smem_raw);                    // RHI+1 weights
+    double *sphi = sw + (RHI + 1);                                        // 2*RHI+1 scratch
+    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));        // TH x GW
+    uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);            // GH x GW
+
+    const int page = blockIdx.z;
+    double sig_est = p.sigma ? p.sigma[page] : 0.0;
+    int radius = 0;
+    double sigma = 0.0;
+    if (sig_est > 1.0) {                       // NaN compares false: no blur
+        sigma = sig_est * 0.1;
+        const double rr = 4.0 * sigma + 0.5;
+        radius = rr > 1.0e6 ? 1000000 : (int)rr;
+    }
+    if (radius > 128) {                        // outside every configuration: flag once
+        if (RLO > 0 && p.err && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicExch(p.err, 1);
+        return;
+    }
+    if (radius < RLO || radius > RHI) return;
+
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (x0 >= p.W || y0 >= p.H) return;
+    const int tid = threadIdx.x;
+
+    if (radius == 0) {
+        for (int idx = tid; idx < TH * TW; idx += 256) {
+            const int y = y0 + idx / TW, x = x0 + idx % TW;
+            if (y < p.H && x < p.W) out[(int64_t)y * p.out_pitch + x] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+        }
+        return;
+    }
+
+    // weights (scipy _gaussian_kernel1d), double; thread-serial so the summation order is fixed
+    if (tid <= 2 * radius) {
+        const int j = tid - radius;
+        const double sigma2 = sigma * sigma;
+        sphi[tid] = exp(__dmul_rn(-0.5 / sigma2, (double)(j * j)));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double sum = np_sum(sphi, 2 * radius + 1);
+        for (int j = 0; j <= radius; j++) sw[j] = sphi[radius + j] / sum;
+    }
+
+    const int gw = TW + 2 * radius, gh = TH + 2 * radius;
+    for (int idx = tid; idx < gh * gw; idx += 256) {
+        const int ly = idx / gw, lx = idx % gw;
+        const int y = reflect_idx(y0 - radius + ly, p.H), x = reflect_idx(x0 - radius + lx, p.W);
+        sg[ly * GW + lx] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+    }
+    __syncthreads();
+
+    // axis 0 (vertical), for every column incl. the horizontal halo
+    for (int idx = tid; idx < TH * gw; idx += 256) {
+        const int ly = idx / gw, lx = idx % gw;
+        const uint8_t *c = sg + (ly + radius) * GW + lx;
+        double acc = __dmul_rn((double)c[0], sw[0]);
+        for (int j = radius; j >= 1; j--)
+            acc = __dadd_rn(acc, __dmul_rn((double)((int)c[-j * GW] + (int)c[j * GW]), sw[j]));
+        stmp[ly * GW + lx] = __double2float_rn(acc);
+    }
+    __syncthreads();
+
+    // axis 1 (horizontal) + uint8 truncation
+    for (int idx = tid; idx < TH * TW; idx += 256) {
+        const int ly = idx / TW, lx = idx % TW;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y >= p.H || x >= p.W) continue;
+        const float *c = stmp + ly * GW + lx + radius;
+        double acc = __dmul_rn((double)c[0], sw[0]);
+        for (int j = radius; j >= 1; j--)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)c[-j], (double)c[j]), sw[j]));
+        const float f = __double2float_rn(acc);
+        out[(int64_t)y * p.out_pitch + x] = (uint8_t)(int)f;          // astype(uint8): truncation
+    }
+}
+
+template <int RHI, int TH, int TW>
+constexpr size_t gray_blur_smem()
+{
+    return sizeof(double) * (RHI + 1) + sizeof(double) * (2 * RHI + 1) + sizeof(float) * TH * (TW + 2 * RHI) +
+           (size_t)(TH + 2 * RHI) * (TW + 2 * RHI);
+}
+
+}  // namespace
+
+int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C,
+                     uint8_t *out, int64_t out_pitch, int64_t out_stride,
+                     int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st)
+{
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag};
+    {
+        constexpr int TH = 32, TW = 128, RHI = 16;
+        constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<0, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
+        k_gray_blur<0, RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        B200MRC_LAUNCH_CHECK();
+    }
+    if (sigma) {
+        constexpr int TH = 16, TW = 32, RHI = 128;
+        constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<17, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
+        k_gray_blur<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        B200MRC_LAUNCH_CHECK();
+    }
+    return B200MRC_OK;
+}
+
+}  // namespace b200mrc
+
+using namespace b200mrc;
+
+extern "C" int b200mrc_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_page_stride, int channels,
+                                 uint8_t *gray_out, int64_t gray_pitch, int64_t gray_page_stride,
+                                 int width, int height, int n_pages, const double *sigma, void *stream)
+{
+    if (!in || !gray_out || width <= 0 || height <= 0 || n_pages <= 0) return B200MRC_ERR_INVALID;
+    if (channels != 1 && channels != 3) return B200MRC_ERR_UNSUPPORTED;
+    if (n_pages > 65535) return B200MRC_ERR_UNSUPPORTED;
+    return launch_gray_blur(in, in_pitch, in_page_stride, channels, gray_out, gray_pitch, gray_page_stride,
+                            width, height, n_pages, sigma, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200mrc_rgb2gray(const uint8_t *rgb, int64_t rgb_pitch, int64_t rgb_page_stride,
+                                uint8_t *gray, int64_t gray_pitch, int64_t gray_page_stride,
+                                int width, int height, int n_pages, void *stream)
+{
+    return b200mrc_gray_blur(rgb, rgb_pitch, rgb_page_stride, 3, gray, gray_pitch, gray_page_stride,
+                             width, height, n_pages, nullptr, stream);
+}

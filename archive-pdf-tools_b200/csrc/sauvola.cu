@@ -1,0 +1,243 @@
+// sauvola.cu -- k_sauvola_mask: Sauvola local-adaptive threshold (reference: binarise_sauvola,
+// cython/sauvola.pyx:29-222, called through threshold_image, internetarchivepdf/mrc.py:58-87).
+//
+// Semantics (closed form of the reference's running sums, see oracle/mrc_oracle.c orc_sauvola):
+//   window rows [max(0,y-o+1), min(H,y+u+1)), cols [max(0,x-l+1), min(W,x+r+1)),
+//   l=(ww+1)/2, r=ww/2, o=(wh+1)/2, u=wh/2;  n = rows*cols
+//   m = (double)(S/n), v = (double)(Q/n) - m*m  (integer divisions, sauvola.pyx:144-145)
+//   t = p + m*(k-1);  fg = t<=0 || t*t <= ((m*m)*k2)*v          (sauvola.pyx:146-147)
+//   every double operation individually rounded (no FMA): the reference build is x86-64 SSE2.
+//
+// B200 mapping: one CTA marches a (column strip x row band) of one page top to bottom.
+//   * each of the 256 threads owns 4 adjacent input columns and keeps their running column sums
+//     (sum, sum of squares over the window's rows) in registers; per output row it adds the
+//     entering row and subtracts the leaving row (32-bit vector loads, L2-resident re-reads);
+//   * the horizontal window sum is a difference of two entries of the per-row prefix of the
+//     column sums: thread-local prefix -> warp-shuffle inclusive scan -> 8 warp totals in smem;
+//     prefixes are published in a bank-conflict-free SoA layout (column c -> [c&3][c>>2]);
+//   * uint32 wrap-around arithmetic is exact because every window sum is < 2^32 for w <= 255;
+//   * S/n and Q/n use a float reciprocal with an exact +-1 fix-up; the test runs in FP64 with
+//     __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
+// Algorithmic HBM bytes: 1 B/px read + 1 B/px written.
+#include "common.cuh"
+
+namespace b200mrc {
+
+namespace {
+
+constexpr int ST = 256;          // threads per CTA
+constexpr int SK = 4;            // columns per thread
+constexpr int SE = ST * SK;      // input columns covered by one CTA (strip + window halo)
+
+struct SauvolaParams {
+    const uint8_t *in; int64_t in_pitch, in_stride;
+    uint8_t *out;      int64_t out_pitch, out_stride;
+    int W, H;
+    int l, r, o, u;
+    int n_strips, strip_w, ext_left, n_bands, band_h;
+    double km1, k2;
+    int kneg, flags;
+};
+
+__device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx, int W)
+{
+    // 4 pixels gx..gx+3 (gx % 4 == 0); pixels outside [0, W) read as 0
+    if (gx < 0 || gx >= W) return 0u;
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+    int valid = W - gx;                  // >= 1
+    if (valid < 4) w &= (1u << (8 * valid)) - 1u;
+    return w;
+}
+
+// floor(a / n) for a < 2^32, n >= 1, a / n <= 65025, rn ~= 1/n (relative error <= 2^-22)
+__device__ __forceinline__ uint32_t div_fix(uint32_t a, uint32_t n, float rn)
+{
+    uint32_t q = (uint32_t)(__uint2float_rz(a) * rn);
+    uint32_t prod = q * n;
+    if (prod > a) { q--; prod -= n; }
+    if (a - prod >= n) q++;
+    return q;
+}
+
+__global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
+{
+    // prefix of column sums for the current row, SoA layout, double buffered
+    __shared__ uint2 sP[2][SK * (ST + 1)];
+    __shared__ uint2 sWT[2][ST / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
+    const int page = blockIdx.y;
+    const int sx0 = strip * p.strip_w;
+    const int ex0 = sx0 - p.ext_left;             // first input column of this CTA (multiple of 4)
+    const int by0 = band * p.band_h;
+    const int by1 = min(p.H, by0 + p.band_h);
+    const int W = p.W, H = p.H;
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride;
+
+    const int i0 = tid * SK;                      // local column of this thread's first pixel
+    const int gx = ex0 + i0;                      // global column (multiple of 4, may be < 0 or >= W)
+    const bool is_out = (gx >= sx0) && (gx < sx0 + p.strip_w) && (gx < W);
+
+    uint32_t cs[SK], cq[SK];
+#pragma unroll
+    for (int j = 0; j < SK; j++) { cs[j] = 0; cq[j] = 0; }
+
+    // ---- band warm-up: column sums over the window rows of the first output row
+    {
+        const int r0 = max(0, by0 - p.o + 1), r1 = min(H - 1, by0 + p.u);
+        for (int yy = r0; yy <= r1; yy++) {
+            uint32_t w = load_word_clamped(in + (int64_t)yy * p.in_pitch, gx, W);
+#pragma unroll
+            for (int j = 0; j < SK; j++) {
+                uint32_t v = (w >> (8 * j)) & 0xFFu;
+                cs[j] += v; cq[j] += v * v;
+            }
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            for (int j = 0; j < SK; j++) sP[b][j * (ST + 1)] = make_uint2(0u, 0u);   // never used: c=0 slot set below
+    }
+
+    for (int y = by0; y < by1; y++) {
+        const int buf = (y - by0) & 1;
+        // issue the loads this iteration needs early
+        const uint32_t wcur = load_word_clamped(in + (int64_t)y * p.in_pitch, gx, W);
+        const int ye = y + 1 + p.u, yl = y + 1 - p.o;
+        uint32_t wenter = 0, wleave = 0;
+        if (y + 1 < by1) {
+            if (ye < H) wenter = load_word_clamped(in + (int64_t)ye * p.in_pitch, gx, W);
+            if (yl >= 0) wleave = load_word_clamped(in + (int64_t)yl * p.in_pitch, gx, W);
+        }
+
+        // ---- prefix of the column sums across the CTA
+        uint32_t ps[SK], pq[SK];
+        ps[0] = cs[0]; pq[0] = cq[0];
+#pragma unroll
+        for (int j = 1; j < SK; j++) { ps[j] = ps[j - 1] + cs[j]; pq[j] = pq[j - 1] + cq[j]; }
+        uint32_t ws = ps[SK - 1], wq = pq[SK - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t ts = __shfl_up_sync(0xffffffffu, ws, d);
+            uint32_t tq = __shfl_up_sync(0xffffffffu, wq, d);
+            if (lane >= d) { ws += ts; wq += tq; }
+        }
+        if (lane == 31) sWT[buf][warp] = make_uint2(ws, wq);
+        __syncthreads();
+        uint32_t bs = ws - ps[SK - 1], bq = wq - pq[SK - 1];     // exclusive within the warp
+#pragma unroll
+        for (int w2 = 0; w2 < ST / 32; w2++) {
+            uint2 t = sWT[buf][w2];
+            if (w2 < warp) { bs += t.x; bq += t.y; }
+        }
+        // inclusive prefix up to local column c-1 is stored at "c": column c -> [c&3][c>>2]
+#pragma unroll
+        for (int j = 0; j < SK; j++) {
+            const int c = i0 + j + 1;
+            sP[buf][(c & 3) * (ST + 1) + (c >> 2)] = make_uint2(bs + ps[j], bq + pq[j]);
+        }
+        if (tid == 0) sP[buf][0] = make_uint2(0u, 0u);            // c = 0: empty prefix
+        __syncthreads();
+
+        // ---- per-pixel test
+        if (is_out) {
+            const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < SK; j++) {
+                const int x = gx + j;
+                const int i = i0 + j;
+                const int chi = i + p.r + 1, clo = i - p.l + 1;
+                const uint2 hi = sP[buf][(chi & 3) * (ST + 1) + (chi >> 2)];
+                const uint2 lo = sP[buf][(clo & 3) * (ST + 1) + (clo >> 2)];
+                const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
+                const int nx = min(W, x + p.r + 1) - max(0, x - p.l + 1);
+                const uint32_t n = (uint32_t)(nx * ny);
+                uint32_t fg = 0;
+                if (x < W && n > 0) {
+                    const float rn = __frcp_rn((float)n);
+                    const uint32_t m = div_fix(S, n, rn);
+                    const uint32_t qn = div_fix(Q, n, rn);
+                    const int v = (int)qn - (int)(m * m);
+                    const double md = (double)m;
+                    const double mm = (double)(m * m);
+                    const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
+                    const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
+                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), (double)v);
+                    const double lhs = __dmul_rn(t, t);
+                    if (p.kneg) fg = (t <= 0.0) && (lhs >= rhs);
+                    else        fg = (t <= 0.0) || (lhs <= rhs);
+                }
+                bits |= fg << (8 * j);
+            }
+            if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) bits ^= 0x01010101u;
+            uint8_t *orow = out + (int64_t)y * p.out_pitch + gx;
+            if (gx + 3 < W) {
+                uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
+                if (p.flags & B200MRC_SAUVOLA_OR_INTO) bits |= *o32;
+                *o32 = bits;
+            } else {
+                for (int j = 0; j < SK && gx + j < W; j++) {
+                    uint8_t b = (uint8_t)((bits >> (8 * j)) & 0xFFu);
+                    if (p.flags & B200MRC_SAUVOLA_OR_INTO) b |= orow[j];
+                    orow[j] = b;
+                }
+            }
+        }
+
+        // ---- slide the window rows for the next output row
+#pragma unroll
+        for (int j = 0; j < SK; j++) {
+            const uint32_t a = (wenter >> (8 * j)) & 0xFFu, b = (wleave >> (8 * j)) & 0xFFu;
+            cs[j] += a - b;
+            cq[j] += a * a - b * b;
+        }
+    }
+}
+
+}  // namespace
+
+}  // namespace b200mrc
+
+using namespace b200mrc;
+
+extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_page_stride,
+                               uint8_t *out, int64_t out_pitch, int64_t out_page_stride,
+                               int width, int height, int n_pages,
+                               int window_width, int window_height, double k, double R,
+                               int flags, void *stream)
+{
+    if (!in || !out || width <= 0 || height <= 0 || n_pages <= 0 || !(R > 0)) return B200MRC_ERR_INVALID;
+    if (window_width < 1 || window_height < 1 || window_width > B200MRC_MAX_WINDOW ||
+        window_height > B200MRC_MAX_WINDOW)
+        return B200MRC_ERR_UNSUPPORTED;
+    if (n_pages > 65535) return B200MRC_ERR_UNSUPPORTED;
+    if ((in_pitch & 3) || (out_pitch & 3) || ((uintptr_t)in & 3) || ((uintptr_t)out & 3) ||
+        (in_page_stride & 3) || (out_page_stride & 3) || in_pitch < width || out_pitch < width)
+        return B200MRC_ERR_ALIGNMENT;
+
+    SauvolaParams p;
+    p.in = in; p.in_pitch = in_pitch; p.in_stride = in_page_stride;
+    p.out = out; p.out_pitch = out_pitch; p.out_stride = out_page_stride;
+    p.W = width; p.H = height;
+    p.l = (window_width + 1) / 2;  p.r = window_width / 2;
+    p.o = (window_height + 1) / 2; p.u = window_height / 2;
+    p.ext_left = (p.l - 1 + 3) / 4 * 4;
+    const int sw_max = (SE - p.ext_left - p.r) / 4 * 4;          // >= 768
+    p.n_strips = cdiv(width, sw_max);
+    p.strip_w = (cdiv(width, p.n_strips) + 3) / 4 * 4;
+    p.band_h = 128;
+    p.n_bands = cdiv(height, p.band_h);
+    p.km1 = k - 1.0;
+    p.k2 = k * k / R / R;                                         // sauvola.pyx:60
+    p.kneg = k < 0;
+    p.flags = flags;
+
+    dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_pages);
+    k_sauvola_mask<<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+    B200MRC_LAUNCH_CHECK();
+    return B200MRC_OK;
+}

@@ -1,0 +1,272 @@
+"""Host side of the B200 MRC engine: device buffers (torch is only the allocator / stream /
+copy plumbing), the batched device-resident API used for throughput runs, and numpy-in /
+numpy-out helpers used by the reference-facing surface in mrc.py and the drop-in shims.
+
+Layout in HBM: a batch is N equally-shaped pages; every plane is "pitched":
+uint8 tensor [N, H, pitch] with pitch = round_up(W*C, 16) so rows are 16-byte aligned
+(vector loads / TMA-legal); masks are one byte per pixel (numpy bool compatible).
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+DENOISE_NONE, DENOISE_FAST, DENOISE_BREGMAN = 'none', 'fast', 'bregman'      # const.py:31-33
+BICUBIC, LANCZOS = 0, 1
+
+
+def _align(v, a=16):
+    return (v + a - 1) // a * a
+
+
+def window_for_dpi(dpi):
+    """threshold_image's window rule, internetarchivepdf/mrc.py:70-75."""
+    window_size = 51
+    if dpi is not None:
+        window_size = int(dpi / 4)
+        if window_size % 2 == 0:
+            window_size += 1
+    return window_size
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise L.B200MrcError('no CUDA device: the b200mrc engine has no CPU fallback')
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plane:
+    """Pitched uint8 device plane batch [N, H, pitch]."""
+
+    def __init__(self, n, h, w, c=1, device=None):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        self.pitch = _align(w * c)
+        self.t = torch.empty((n, h, self.pitch), dtype=torch.uint8, device=device or 'cuda')
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.t.data_ptr())
+
+    @property
+    def page_stride(self):
+        return self.h * self.pitch
+
+    def view(self):
+        """[N, H, W*C] strided view without the row padding."""
+        return self.t[:, :, : self.w * self.c]
+
+    def upload(self, host, non_blocking=True):
+        """host: uint8/bool ndarray or CPU tensor [N,H,W] / [N,H,W,C] (pinned for async copies)."""
+        ht = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host).view(np.uint8))
+        ht = ht.reshape(self.n, self.h, self.w * self.c)
+        if self.pitch == self.w * self.c:
+            self.t.copy_(ht, non_blocking=non_blocking)
+        else:
+            self.view().copy_(ht.to(self.t.device, non_blocking=non_blocking))
+        return self
+
+    def download(self, out=None, non_blocking=False):
+        """-> CPU tensor [N,H,W*C] (into `out` if given, e.g. a pinned buffer)."""
+        src = self.view()
+        if self.pitch != self.w * self.c:
+            src = src.contiguous()
+        if out is None:
+            return src.cpu()
+        out.reshape(self.n, self.h, self.w * self.c).copy_(src, non_blocking=non_blocking)
+        return out
+
+    def numpy(self, dtype=np.uint8):
+        a = self.download().numpy()
+        shape = (self.n, self.h, self.w) + ((self.c,) if self.c > 1 else ())
+        return a.reshape(shape).view(dtype)
+
+
+class ThumbnailPlan:
+    """PIL Image.thumbnail((int(w/f), int(h/f))) plan (mrc.py:420-434 / 454-468)."""
+
+    def __init__(self, w, h, c, req_w, req_h, reducing_gap=2.0, filter=BICUBIC):
+        st = C.c_int(0)
+        self.handle = L.lib().b200mrc_thumbnail_plan_create(w, h, c, float(req_w), float(req_h),
+                                                            float(reducing_gap or 0.0), filter, C.byref(st))
+        if not self.handle:
+            L.check(st.value, 'b200mrc_thumbnail_plan_create')
+            self.noop = True
+            self.out_w, self.out_h = w, h
+        else:
+            self.noop = False
+            ow, oh = C.c_int(0), C.c_int(0)
+            L.lib().b200mrc_resample_plan_out_size(self.handle, C.byref(ow), C.byref(oh))
+            self.out_w, self.out_h = ow.value, oh.value
+        self.c = c
+
+    def workspace_bytes(self, n):
+        return 0 if self.noop else L.lib().b200mrc_resample_workspace_bytes(self.handle, n)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                L.lib().b200mrc_resample_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def downsample_plan(w, h, c, factor, filter=BICUBIC):
+    """The reference's guard + thumbnail call: returns (plan_or_None, too_small)."""
+    if factor is None:
+        return None, False
+    wd, hd = int(w / factor), int(h / factor)
+    if wd > 0 and hd > 0:
+        plan = ThumbnailPlan(w, h, c, wd, hd, 2.0, filter)
+        return (None if plan.noop else plan), False
+    return None, True
+
+
+class _Workspace:
+    def __init__(self):
+        self.t = None
+
+    def get(self, nbytes, device):
+        if self.t is None or self.t.numel() < nbytes or self.t.device != torch.device(device):
+            self.t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.t
+
+
+class MrcEngine:
+    """One engine per process/GPU.  Methods taking `Plane`s are asynchronous on the current stream."""
+
+    def __init__(self, device=None):
+        _require_cuda()
+        L.lib()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self._ws = _Workspace()
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ raw stages (device planes)
+    def workspace(self, nbytes):
+        t = self._ws.get(nbytes, self.device)
+        return C.c_void_p(t.data_ptr()), t.numel()
+
+    def sauvola(self, gray, out, window_w, window_h=None, k=0.34, R=128.0, flags=0):
+        L.check(L.lib().b200mrc_sauvola(gray.ptr, gray.pitch, gray.page_stride, out.ptr, out.pitch, out.page_stride,
+                                        gray.w, gray.h, gray.n, window_w, window_h or window_w, float(k), float(R),
+                                        flags, _stream_ptr()), 'b200mrc_sauvola')
+
+    def gray_blur(self, img, gray, sigma_dev=None):
+        sp = C.c_void_p(sigma_dev.data_ptr()) if sigma_dev is not None else None
+        L.check(L.lib().b200mrc_gray_blur(img.ptr, img.pitch, img.page_stride, img.c, gray.ptr, gray.pitch,
+                                          gray.page_stride, img.w, img.h, img.n, sp, _stream_ptr()), 'b200mrc_gray_blur')
+
+    def estimate_noise(self, img):
+        """-> float64 device tensor [N] (mrc.py:273-296 on every page)."""
+        sigma = torch.empty(img.n, dtype=torch.float64, device=self.device)
+        need = L.lib().b200mrc_noise_workspace_bytes(img.w, img.h, img.n)
+        wp, wb = self.workspace(need)
+        L.check(L.lib().b200mrc_estimate_noise(img.ptr, img.pitch, img.page_stride, img.c, img.w, img.h, img.n,
+                                               C.c_void_p(sigma.data_ptr()), wp, wb, _stream_ptr()), 'b200mrc_estimate_noise')
+        return sigma
+
+    def denoise(self, mask, mincnt=4, n_size=2):
+        need = L.lib().b200mrc_denoise_workspace_bytes(mask.w, mask.h, mask.n)
+        wp, wb = self.workspace(need)
+        L.check(L.lib().b200mrc_denoise(mask.ptr, mask.pitch, mask.page_stride, mask.w, mask.h, mask.n, mincnt, n_size,
+                                        wp, wb, _stream_ptr()), 'b200mrc_denoise')
+
+    def optimise(self, mask, img, out_fg=None, n_fg=3, out_bg=None, n_bg=10):
+        need = L.lib().b200mrc_optimise_workspace_bytes(img.w, img.h, img.n)
+        wp, wb = self.workspace(need)
+        f = (out_fg.ptr, out_fg.pitch, out_fg.page_stride) if out_fg is not None else (None, 0, 0)
+        b = (out_bg.ptr, out_bg.pitch, out_bg.page_stride) if out_bg is not None else (None, 0, 0)
+        L.check(L.lib().b200mrc_optimise(mask.ptr, mask.pitch, mask.page_stride, img.ptr, img.pitch, img.page_stride, img.c,
+                                         f[0], f[1], f[2], n_fg, b[0], b[1], b[2], n_bg, img.w, img.h, img.n,
+                                         wp, wb, _stream_ptr()), 'b200mrc_optimise')
+
+    def resample(self, plan, src, dst):
+        need = plan.workspace_bytes(src.n)
+        wp, wb = self.workspace(need)
+        L.check(L.lib().b200mrc_resample(plan.handle, src.ptr, src.pitch, src.page_stride, dst.ptr, dst.pitch,
+                                         dst.page_stride, src.n, wp, wb, _stream_ptr()), 'b200mrc_resample')
+
+    # ------------------------------------------------------------------ whole pipeline, device resident
+    def make_batch(self, n, h, w, c, bg_downsample=None, fg_downsample=None, mask_only=False):
+        """Allocates the input/output planes and the workspace of a batch; returns a DecomposeBatch."""
+        return DecomposeBatch(self, n, h, w, c, bg_downsample, fg_downsample, mask_only)
+
+    # ------------------------------------------------------------------ numpy helpers (one-shot)
+    def threshold_image_np(self, img, window, k=0.34, R=128.0, raw_inverted=False):
+        h, w = img.shape
+        src = Plane(1, h, w, 1, self.device).upload(img[None], non_blocking=False)
+        dst = Plane(1, h, w, 1, self.device)
+        self.sauvola(src, dst, window, window, k, R, L.SAUVOLA_RAW_INVERTED if raw_inverted else 0)
+        return dst.numpy(np.bool_)[0]
+
+
+class DecomposeBatch:
+    """Device-resident state of one batch of pages going through create_mrc_hocr_components."""
+
+    def __init__(self, eng, n, h, w, c, bg_downsample=None, fg_downsample=None, mask_only=False):
+        self.eng, self.n, self.h, self.w, self.c = eng, n, h, w, c
+        dev = eng.device
+        self.mask_only = mask_only
+        self.errors = set()
+        self.img = Plane(n, h, w, c, dev)
+        self.mask = Plane(n, h, w, 1, dev)
+        self.sigma = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.sigma_in = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.fg_plan = self.bg_plan = None
+        self.fg = self.bg = None
+        if not mask_only:
+            self.fg_plan, small_f = downsample_plan(w, h, c, fg_downsample)
+            self.bg_plan, small_b = downsample_plan(w, h, c, bg_downsample)
+            if small_f or small_b:
+                self.errors.add('too-small-to-downsample')       # const.py:38, mrc.py:430-431, 464-465
+            fw, fh = (self.fg_plan.out_w, self.fg_plan.out_h) if self.fg_plan else (w, h)
+            bw, bh = (self.bg_plan.out_w, self.bg_plan.out_h) if self.bg_plan else (w, h)
+            self.fg = Plane(n, fh, fw, c, dev)
+            self.bg = Plane(n, bh, bw, c, dev)
+        self._args = None
+        self._ws = None
+
+    def _build_args(self, window, k, R, denoise_fast, use_sigma_in):
+        a = L.DecomposeArgs()
+        a.img, a.img_pitch, a.img_page_stride, a.channels = self.img.ptr, self.img.pitch, self.img.page_stride, self.c
+        a.width, a.height, a.n_pages = self.w, self.h, self.n
+        a.window, a.k, a.R = window, k, R
+        a.flags = (L.DECOMPOSE_DENOISE_FAST if denoise_fast else 0) | (L.DECOMPOSE_MASK_ONLY if self.mask_only else 0) | \
+                  (L.DECOMPOSE_NO_NOISE_EST if use_sigma_in else 0)
+        a.sigma_in = C.c_void_p(self.sigma_in.data_ptr()) if use_sigma_in else None
+        a.sigma_out = C.c_void_p(self.sigma.data_ptr())
+        a.mask, a.mask_pitch, a.mask_page_stride = self.mask.ptr, self.mask.pitch, self.mask.page_stride
+        if not self.mask_only:
+            a.fg, a.fg_pitch, a.fg_page_stride = self.fg.ptr, self.fg.pitch, self.fg.page_stride
+            a.bg, a.bg_pitch, a.bg_page_stride = self.bg.ptr, self.bg.pitch, self.bg.page_stride
+            a.fg_plan = self.fg_plan.handle if self.fg_plan else None
+            a.bg_plan = self.bg_plan.handle if self.bg_plan else None
+        need = L.lib().b200mrc_decompose_workspace_bytes(C.byref(a))
+        if need == 0:
+            raise L.B200MrcError('b200mrc_decompose: invalid arguments')
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.eng.device)
+        a.workspace, a.workspace_bytes = C.c_void_p(self._ws.data_ptr()), self._ws.numel()
+        return a
+
+    def run(self, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST, sigma=None):
+        """Enqueue the whole pipeline (b200mrc_decompose) on the current stream.  `sigma`: optional
+        per-page injected sigma_est (host sequence) replacing the on-device estimate."""
+        if denoise_mask not in (DENOISE_NONE, DENOISE_FAST):
+            if denoise_mask == DENOISE_BREGMAN:
+                raise NotImplementedError('denoise_bregman is out of scope (SURVEY.md section 2)')
+            raise ValueError('Invalid denoise option:', denoise_mask)              # mrc.py:396
+        if sigma is not None:
+            self.sigma_in.copy_(torch.as_tensor(np.asarray(sigma, np.float64)))
+        key = (window, k, R, denoise_mask == DENOISE_FAST, sigma is not None)
+        if self._args is None or self._args[0] != key:
+            self._args = (key, self._build_args(window, k, R, denoise_mask == DENOISE_FAST, sigma is not None))
+        L.check(L.lib().b200mrc_decompose(C.byref(self._args[1]), _stream_ptr()), 'b200mrc_decompose')
+        return self

@@ -1,0 +1,66 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def orc():
+    """The CPU oracle (test infrastructure; see oracle/mrc_oracle.c)."""
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope='session')
+def refmods():
+    """The reference's own compiled Cython (oracle/_ref), or skip when it was never built."""
+    from oracle import ref_pipeline
+    mods = ref_pipeline.ref_modules()
+    if mods is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference once, see oracle/build_ref.py)')
+    return mods
+
+
+@pytest.fixture(scope='session')
+def synth():
+    import archive_pdf_tools_b200.synth as s
+    return s
+
+
+@pytest.fixture(scope='session')
+def eng():
+    import torch
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device (no CPU fallback exists)'
+    import archive_pdf_tools_b200 as pkg
+    return pkg.get_engine()
+
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def golden_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+
+
+def load_golden(name, synth):
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    idx, H, W, dpi, rgb, ht, bgd, fgd = (int(v) for v in z['params'])
+    dpi = None if dpi < 0 else dpi
+    page = synth.make_page(idx, H, W, dpi=dpi or 200, rgb=bool(rgb), sigma_n=float(z['sigma_n']), halftone=bool(ht))
+    g = dict(page=page, dpi=dpi, bg_downsample=None if bgd < 0 else bgd, fg_downsample=None if fgd < 0 else fgd,
+             denoise=str(z['denoise']), sigma=float(z['sigma']), fg=z['fg'], bg=z['bg'],
+             mask=np.unpackbits(z['mask'])[: H * W].reshape(H, W).astype(bool),
+             t33=np.unpackbits(z['t33'])[: H * W].reshape(H, W).astype(bool),
+             t01=np.unpackbits(z['t01'])[: H * W].reshape(H, W).astype(bool),
+             timing_keys=[str(k) for k in z['timing_keys']])
+    return g

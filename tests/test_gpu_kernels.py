@@ -1,0 +1,212 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (libb200mrc.so) against the CPU oracle.
+Bar: bit-exact for every integer/byte result (masks, gray, fg/bg, thumbnails, sigma)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _plane(eng, arr, c=None):
+    from archive_pdf_tools_b200 import Plane
+    a = np.ascontiguousarray(arr)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    if c is None:
+        c = a.shape[3] if a.ndim == 4 else 1
+    n, h, w = a.shape[:3]
+    return Plane(n, h, w, c, eng.device).upload(a, non_blocking=False)
+
+
+def _empty(eng, n, h, w, c=1):
+    from archive_pdf_tools_b200 import Plane
+    return Plane(n, h, w, c, eng.device)
+
+
+def _imgs(rng, h, w):
+    return [rng.integers(0, 256, (h, w), dtype=np.uint8),
+            (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8),
+            np.clip(rng.normal(200, 30, (h, w)), 0, 255).astype(np.uint8),
+            np.full((h, w), 255, np.uint8), np.zeros((h, w), np.uint8),
+            ((np.add.outer(np.arange(h), np.arange(w)) % 2) * 255).astype(np.uint8)]
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (3, 7), (10, 10), (40, 200), (200, 40), (77, 133), (300, 1003), (131, 2000)])
+def test_sauvola_matches_oracle(eng, orc, shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    imgs = np.stack(_imgs(rng, h, w))
+    src = _plane(eng, imgs)
+    dst = _empty(eng, len(imgs), h, w)
+    for ww, wh, k in [(3, 3, 0.34), (33, 33, 0.34), (51, 51, 0.1), (101, 101, 0.34), (151, 151, 0.2), (255, 255, 0.34),
+                      (33, 51, 0.34), (4, 6, 0.5), (75, 75, -0.2)]:
+        eng.sauvola(src, dst, ww, wh, k=k)
+        got = dst.numpy(np.bool_)
+        for i in range(len(imgs)):
+            exp = orc.sauvola(imgs[i], ww, wh, k=k)
+            assert np.array_equal(got[i], exp), (shape, ww, wh, k, i, int((got[i] != exp).sum()))
+
+
+def test_sauvola_flags_and_R(eng, orc):
+    from archive_pdf_tools_b200 import _lib
+    rng = np.random.default_rng(5)
+    img = np.clip(rng.normal(170, 50, (1, 90, 150)), 0, 255).astype(np.uint8)
+    src = _plane(eng, img)
+    dst = _empty(eng, 1, 90, 150)
+    exp = orc.sauvola(img[0], 33, k=0.34, R=100.0)
+    eng.sauvola(src, dst, 33, k=0.34, R=100.0)
+    assert np.array_equal(dst.numpy(np.bool_)[0], exp)
+    eng.sauvola(src, dst, 33, k=0.34, R=100.0, flags=_lib.SAUVOLA_RAW_INVERTED)
+    assert np.array_equal(dst.numpy(np.bool_)[0], ~exp)
+    pre = rng.random((1, 90, 150)) < 0.2
+    dst.upload(pre, non_blocking=False)
+    eng.sauvola(src, dst, 33, k=0.34, R=100.0, flags=_lib.SAUVOLA_OR_INTO)
+    assert np.array_equal(dst.numpy(np.bool_)[0], exp | pre[0])
+
+
+def test_rgb2gray_all_colours(eng, orc):
+    allc = np.stack(np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij'), -1)
+    allc = allc.reshape(1, 4096, 4096, 3).astype(np.uint8)
+    src = _plane(eng, allc)
+    g = _empty(eng, 1, 4096, 4096)
+    eng.gray_blur(src, g, None)
+    assert np.array_equal(g.numpy()[0], orc.rgb2gray(allc[0]))
+
+
+@pytest.mark.parametrize('shape,rgb', [((64, 64), False), ((2, 9), False), ((3, 3), True), ((1, 1), False), ((330, 255), True), ((513, 771), False)])
+def test_noise_sigma_matches_oracle(eng, orc, synth, shape, rgb):
+    h, w = shape
+    pages = np.stack([synth.make_page(i, h, w, dpi=100, rgb=rgb, sigma_n=s) for i, s in enumerate((0.0, 0.7, 3.0, 12.0))])
+    src = _plane(eng, pages)
+    got = eng.estimate_noise(src).cpu().numpy()
+    for i in range(len(pages)):
+        gray = pages[i] if not rgb else orc.rgb2gray(pages[i])
+        exp = orc.estimate_noise(gray)
+        assert (np.isnan(exp) and np.isnan(got[i])) or got[i] == exp, (shape, i, got[i], exp)
+
+
+def test_noise_sigma_flat_page_is_nan(eng, orc):
+    src = _plane(eng, np.full((1, 40, 40), 128, np.uint8))
+    got = eng.estimate_noise(src).cpu().numpy()[0]
+    exp = orc.estimate_noise(np.full((40, 40), 128, np.uint8))
+    assert (np.isnan(got) and np.isnan(exp)) or got == exp
+
+
+@pytest.mark.parametrize('shape,rgb', [((1, 1), False), ((5, 9), True), ((60, 80), False), ((151, 260), True)])
+def test_gray_blur_matches_oracle(eng, orc, shape, rgb):
+    import torch
+    h, w = shape
+    rng = np.random.default_rng(h + w)
+    sig_est = [0.5, 1.0, 1.1, 1.3, 3.7, 9.0, 21.0, 41.0, 44.0, 90.0, float('nan')]
+    n = len(sig_est)
+    pages = rng.integers(0, 256, (n, h, w, 3) if rgb else (n, h, w), dtype=np.uint8)
+    src = _plane(eng, pages)
+    dst = _empty(eng, n, h, w)
+    eng.gray_blur(src, dst, torch.tensor(sig_est, dtype=torch.float64, device=eng.device))
+    got = dst.numpy()
+    for i, s in enumerate(sig_est):
+        gray = pages[i] if not rgb else orc.rgb2gray(pages[i])
+        exp = gray
+        if s > 1.0:
+            exp = orc.gauss_blur(gray.astype(np.float32), s * 0.1).astype(np.uint8)
+        assert np.array_equal(got[i], exp), (shape, s, int((got[i] != exp).sum()))
+
+
+def _masks(rng, h, w):
+    ms = [rng.random((h, w)) < d for d in (0.02, 0.1, 0.3, 0.6, 0.95)]
+    ms.append(np.eye(h, w, dtype=bool) | np.eye(h, w, 1, dtype=bool))
+    ms.append(np.ones((h, w), bool)); ms.append(np.zeros((h, w), bool))
+    d = np.zeros((h, w), bool); d[::3, :] = True; ms.append(d)
+    return ms
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (4, 4), (5, 5), (6, 9), (50, 70), (70, 300), (200, 600), (131, 97), (64, 256), (65, 257)])
+def test_denoise_matches_oracle(eng, orc, shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    ms = np.stack(_masks(rng, h, w))
+    pl = _plane(eng, ms)
+    eng.denoise(pl, 4, 2)
+    got = pl.numpy(np.bool_)
+    for i in range(len(ms)):
+        exp = orc.denoise(ms[i])
+        assert np.array_equal(got[i], exp), (shape, i, int((got[i] != exp).sum()))
+
+
+def test_denoise_long_cascade(eng, orc):
+    # a 2-px diagonal band: every removal exposes the next pixel -> O(H) dependency chain across tiles
+    h, w = 700, 700
+    m = np.zeros((h, w), bool)
+    idx = np.arange(h)
+    m[idx, idx] = True
+    m[idx[:-1], idx[:-1] + 1] = True
+    pl = _plane(eng, m[None])
+    eng.denoise(pl, 4, 2)
+    assert np.array_equal(pl.numpy(np.bool_)[0], orc.denoise(m))
+
+
+@pytest.mark.parametrize('shape,c', [((1, 1), 1), ((2, 3), 3), ((5, 5), 1), ((30, 41), 3), ((64, 200), 3), ((90, 700), 1), ((131, 97), 3)])
+def test_optimise_matches_oracle(eng, orc, shape, c):
+    h, w = shape
+    rng = np.random.default_rng(h * 13 + w)
+    dens = (0.0, 0.05, 0.5, 0.95, 1.0)
+    masks = np.stack([rng.random((h, w)) < d for d in dens])
+    imgs = rng.integers(0, 256, (len(dens), h, w, 3) if c == 3 else (len(dens), h, w), dtype=np.uint8)
+    m = _plane(eng, masks)
+    src = _plane(eng, imgs)
+    fg = _empty(eng, len(dens), h, w, c)
+    bg = _empty(eng, len(dens), h, w, c)
+    for nfg, nbg in [(3, 10), (1, 16), (10, 3)]:
+        eng.optimise(m, src, fg, nfg, bg, nbg)
+        gf, gb = fg.numpy(), bg.numpy()
+        for i in range(len(dens)):
+            ef = orc.optimise(masks[i], imgs[i], nfg)
+            eb = orc.optimise(~masks[i], imgs[i], nbg)
+            assert np.array_equal(gf[i], ef), ('fg', shape, c, nfg, i, int((gf[i] != ef).sum()))
+            assert np.array_equal(gb[i], eb), ('bg', shape, c, nbg, i, int((gb[i] != eb).sum()))
+    eng.optimise(m, src, out_fg=fg, n_fg=5, out_bg=None)          # single reference call form
+    assert np.array_equal(fg.numpy()[2], orc.optimise(masks[2], imgs[2], 5))
+
+
+def test_optimise_text_page_many_strips(eng, orc, synth):
+    page = synth.make_page(9, 500, 1300, dpi=200)
+    gray = orc.rgb2gray(page)
+    mask = orc.denoise(orc.sauvola(gray, 51))
+    m = _plane(eng, mask[None]); src = _plane(eng, page[None])
+    fg = _empty(eng, 1, 500, 1300, 3); bg = _empty(eng, 1, 500, 1300, 3)
+    eng.optimise(m, src, fg, 3, bg, 10)
+    assert np.array_equal(fg.numpy()[0], orc.optimise(mask, page, 3))
+    assert np.array_equal(bg.numpy()[0], orc.optimise(~mask, page, 10))
+
+
+@pytest.mark.parametrize('shape', [(33, 25), (100, 77), (330, 255), (64, 64), (7, 5), (600, 450)])
+def test_thumbnail_matches_oracle_and_pillow(eng, orc, shape):
+    from PIL import Image
+    from archive_pdf_tools_b200 import ThumbnailPlan
+    h, w = shape
+    rng = np.random.default_rng(h + 3 * w)
+    for f in [2, 3, 4, 5, 6, 8, 1.5, 2.5]:
+        for ch in (1, 3):
+            imgs = rng.integers(0, 256, (2, h, w, 3) if ch == 3 else (2, h, w), dtype=np.uint8)
+            wd, hd = int(w / f), int(h / f)
+            if wd <= 0 or hd <= 0:
+                continue
+            exp = orc.thumbnail(imgs[1], wd, hd)
+            im = Image.fromarray(imgs[1]); im.thumbnail((wd, hd))
+            assert np.array_equal(exp, np.array(im))
+            plan = ThumbnailPlan(w, h, ch, wd, hd)
+            if plan.noop:
+                assert exp.shape[:2] == (h, w)
+                continue
+            assert (plan.out_h, plan.out_w) == exp.shape[:2], (shape, f)
+            src = _plane(eng, imgs)
+            dst = _empty(eng, 2, plan.out_h, plan.out_w, ch)
+            eng.resample(plan, src, dst)
+            assert np.array_equal(dst.numpy()[1], exp), (shape, f, ch)
+
+
+def test_special_gray_matches_oracle(eng, orc, synth):
+    import archive_pdf_tools_b200 as pkg
+    rng = np.random.default_rng(4)
+    for img in (synth.make_page(2, 200, 150, dpi=100), rng.integers(0, 256, (97, 131, 3), dtype=np.uint8),
+                rng.integers(40, 200, (64, 64, 3), dtype=np.uint8)):
+        assert np.array_equal(pkg.special_gray_convert(img), orc.special_gray_convert(img))

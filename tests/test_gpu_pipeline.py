@@ -1,0 +1,158 @@
+"""GPU parity tests of the whole path: the reference-facing surface (generator, threshold_image,
+drop-in modules) and the batched C-ABI pipeline, against golden reference outputs and the oracle.
+Bar (BASELINE.json): masks bit-exact; fg/bg within +-1 LSB (we assert exact equality and report)."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_generator_matches_golden_reference(eng, synth, name):
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    g = load_golden(name, synth)
+    timing, errors = [], set()
+    gen = pkg.create_mrc_hocr_components(Image.fromarray(g['page']), [], dpi=g['dpi'], bg_downsample=g['bg_downsample'],
+                                         fg_downsample=g['fg_downsample'], denoise_mask=g['denoise'],
+                                         timing_data=timing, errors=errors)
+    mask = next(gen); fg = next(gen); bg = next(gen)
+    with pytest.raises(StopIteration):
+        next(gen)
+    assert mask.dtype == np.bool_ and fg.dtype == np.uint8 and bg.dtype == np.uint8
+    assert np.array_equal(mask, g['mask']), int((mask != g['mask']).sum())
+    assert fg.shape == g['fg'].shape and bg.shape == g['bg'].shape
+    assert np.abs(fg.astype(int) - g['fg']).max() <= 1 and np.abs(bg.astype(int) - g['bg']).max() <= 1
+    assert np.array_equal(fg, g['fg']) and np.array_equal(bg, g['bg'])
+    assert [k for k, _ in timing] == g['timing_keys']
+    assert errors == set()
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_threshold_image_matches_golden(eng, synth, orc, name):
+    import archive_pdf_tools_b200 as pkg
+    g = load_golden(name, synth)
+    gray = g['page'] if g['page'].ndim == 2 else orc.rgb2gray(g['page'])
+    assert np.array_equal(pkg.threshold_image(gray, 132), g['t33'])
+    assert np.array_equal(pkg.threshold_image(gray, g['dpi'], 0.1), g['t01'])
+
+
+def test_mask_only_generator_stops_after_first_yield(eng, synth, orc):
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    page = synth.make_page(21, 240, 200, dpi=100, rgb=False)
+    gen = pkg.create_mrc_hocr_components(Image.fromarray(page), [], dpi=100, denoise_mask='fast')
+    mask = next(gen)                                   # recode.py:398-407 (--bw-pdf) stops here
+    exp = orc.decompose(page, dpi=100, denoise_mask='fast', mask_only=True)
+    assert np.array_equal(mask, exp['mask'])
+
+
+def test_generator_error_behaviour(eng):
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    im = Image.fromarray(np.full((16, 16), 200, np.uint8))
+    with pytest.raises(ValueError):
+        next(pkg.create_mrc_hocr_components(im, [], dpi=100))                      # denoise_mask=None -> mrc.py:396
+    errs = set()
+    gen = pkg.create_mrc_hocr_components(Image.fromarray(np.full((2, 9), 200, np.uint8)), [], dpi=100, bg_downsample=3,
+                                         denoise_mask='none', errors=errs)
+    out = list(gen)
+    assert errs == {'too-small-to-downsample'} and out[2].shape == (2, 9)
+
+
+def test_palette_mode_goes_through_pil_like_reference(eng, synth, orc):
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    page = synth.make_page(22, 120, 100, dpi=100)
+    im = Image.fromarray(page).convert('P')
+    mask, fg, bg = list(pkg.create_mrc_hocr_components(im, [], dpi=100, bg_downsample=2, denoise_mask='fast'))
+    gray = np.array(im.convert('L')); rgb = np.array(im.convert('RGB'))
+    m, _ = orc.threshold_mask(gray, dpi=100)
+    m = orc.denoise(m)
+    assert np.array_equal(mask, m)
+    assert np.array_equal(fg, orc.optimise(m, rgb, 3))
+    assert np.array_equal(bg, orc.thumbnail(orc.optimise(~m, rgb, 10), 50, 60))
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(n=3, h=330, w=255, rgb=True, dpi=100, bg=3, fg=None, den='fast', sn=3.0, ht=False),
+    dict(n=2, h=300, w=1100, rgb=True, dpi=300, bg=3, fg=None, den='fast', sn=3.0, ht=True),
+    dict(n=4, h=220, w=170, rgb=False, dpi=200, bg=None, fg=None, den='fast', sn=3.0, ht=False),
+    dict(n=2, h=260, w=300, rgb=True, dpi=None, bg=4, fg=2, den='none', sn=10.0, ht=False),
+])
+def test_batched_decompose_matches_oracle(eng, synth, orc, cfg):
+    import archive_pdf_tools_b200 as pkg
+    pages = np.stack([synth.make_page(100 + i, cfg['h'], cfg['w'], dpi=cfg['dpi'] or 200, rgb=cfg['rgb'], sigma_n=cfg['sn'],
+                                      halftone=cfg['ht'] and i % 2 == 0) for i in range(cfg['n'])])
+    res = pkg.decompose_pages(pages, dpi=cfg['dpi'], bg_downsample=cfg['bg'], fg_downsample=cfg['fg'], denoise_mask=cfg['den'])
+    for i in range(cfg['n']):
+        exp = orc.decompose(pages[i], dpi=cfg['dpi'], bg_downsample=cfg['bg'], fg_downsample=cfg['fg'], denoise_mask=cfg['den'])
+        assert res['sigma'][i] == exp['sigma'], (i, res['sigma'][i], exp['sigma'])
+        assert np.array_equal(res['mask'][i], exp['mask']), (i, int((res['mask'][i] != exp['mask']).sum()))
+        assert np.array_equal(res['fg'][i], exp['fg']), i
+        assert np.array_equal(res['bg'][i], exp['bg']), i
+
+
+def test_injected_sigma_and_mask_only(eng, synth, orc):
+    import archive_pdf_tools_b200 as pkg
+    pages = np.stack([synth.make_page(200 + i, 200, 160, dpi=100, rgb=False, sigma_n=2.0) for i in range(3)])
+    sig = [0.3, 2.0, 7.5]
+    res = pkg.decompose_pages(pages, dpi=100, denoise_mask='fast', mask_only=True, sigma=sig)
+    for i in range(3):
+        exp = orc.decompose(pages[i], dpi=100, denoise_mask='fast', mask_only=True, sigma_est=sig[i])
+        assert np.array_equal(res['mask'][i], exp['mask'])
+    assert 'fg' not in res
+
+
+def test_full_size_400dpi_page_matches_oracle(eng, synth, orc):
+    """BASELINE config 2 shape (one page of the 64): 3300x2550 RGB, dpi 400 (window 101), bg/3, denoise fast."""
+    import archive_pdf_tools_b200 as pkg
+    pages = np.stack([synth.make_page(i, 3300, 2550, dpi=400, halftone=(i == 1)) for i in range(2)])
+    res = pkg.decompose_pages(pages, dpi=400, bg_downsample=3, denoise_mask='fast')
+    for i in range(2):
+        exp = orc.decompose(pages[i], dpi=400, bg_downsample=3, denoise_mask='fast')
+        assert res['sigma'][i] == exp['sigma']
+        assert np.array_equal(res['mask'][i], exp['mask']), int((res['mask'][i] != exp['mask']).sum())
+        assert np.array_equal(res['fg'][i], exp['fg'])
+        assert np.array_equal(res['bg'][i], exp['bg']) and res['bg'][i].shape == (1100, 850, 3)
+    # size-independent properties: results do not depend on batch composition / order
+    res1 = pkg.decompose_pages(pages[::-1].copy(), dpi=400, bg_downsample=3, denoise_mask='fast')
+    assert np.array_equal(res1['mask'][1], res['mask'][0]) and np.array_equal(res1['bg'][0], res['bg'][1])
+    # fg equals the page on mask pixels, bg equals the page off the mask (optimiser.pyx copies img first)
+    m = res['mask'][0]
+    assert np.array_equal(res['fg'][0][m], pages[0][m])
+
+
+def test_config1_window33_full_page(eng, synth, orc):
+    import archive_pdf_tools_b200 as pkg
+    page = synth.make_page(0, 3300, 2550, dpi=400, rgb=False)
+    assert np.array_equal(pkg.threshold_image(page, 132), orc.sauvola(page, 33))       # BASELINE config 1
+    assert np.array_equal(pkg.threshold_image(page, 600), orc.sauvola(page, 151))
+
+
+def test_dropin_modules_match_reference_cython(eng, refmods):
+    import archive_pdf_tools_b200 as pkg
+    pkg.install(patch_reference=False)
+    import sauvola, optimiser
+    assert sauvola.__file__.startswith(pkg.DROPIN_DIR) and optimiser.__file__.startswith(pkg.DROPIN_DIR)
+    rsau, ropt = refmods
+    rng = np.random.default_rng(8)
+    h, w = 90, 140
+    img = np.clip(rng.normal(180, 40, (h, w)), 0, 255).astype(np.uint8)
+    o1 = np.empty(h * w, np.uint8); o2 = np.ndarray(h * w, dtype=bool)
+    assert rsau.binarise_sauvola(img.reshape(-1), o1, w, h, 33, 33, 0.34, 128) == 0
+    assert sauvola.binarise_sauvola(img.reshape(-1), o2, w, h, 33, 33, 0.34, 128) == 0
+    assert np.array_equal(o1, o2.view(np.uint8))
+    mask = (rng.random((h, w)) < 0.1)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for n in (3, 10):
+        assert np.array_equal(optimiser.optimise_rgb2(mask.view(np.uint8), rgb, w, h, n), ropt.optimise_rgb2(mask.view(np.uint8), rgb, w, h, n))
+        assert np.array_equal(optimiser.optimise_gray(mask, img, w, h, n), ropt.optimise_gray(mask.view(np.uint8), img, w, h, n))
+    a = mask.copy(); b = mask.copy().view(np.uint8)
+    ret = optimiser.fast_mask_denoise(a, w, h, 4, 2)
+    ropt.fast_mask_denoise(b, w, h, 4, 2)
+    assert ret is a and np.array_equal(a.view(np.uint8), b)
+    with pytest.raises(ValueError):
+        optimiser.optimise_gray2(mask, img.astype(np.float32), w, h, 3)

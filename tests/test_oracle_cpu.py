@@ -1,0 +1,136 @@
+"""CPU suite, part 1: the oracle is pinned before anything trusts it.
+
+* against the reference's OWN compiled Cython (oracle/_ref) on random + adversarial shapes,
+* against the installed third-party libraries the reference calls (Pillow, scipy),
+* against the golden vectors in tests/golden/ (outputs of the imported, unmodified reference).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden
+
+SHAPES = [(1, 1), (3, 7), (10, 10), (40, 200), (200, 40), (77, 133), (129, 257)]
+
+
+def _images(rng, h, w):
+    yield rng.integers(0, 256, (h, w), dtype=np.uint8)
+    yield (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+    yield np.clip(rng.normal(200, 30, (h, w)), 0, 255).astype(np.uint8)
+    yield np.full((h, w), 255, np.uint8)
+    yield np.zeros((h, w), np.uint8)
+    yield ((np.add.outer(np.arange(h), np.arange(w)) % 2) * 255).astype(np.uint8)     # checkerboard
+
+
+def _ref_sauvola(sau, img, ww, wh, k, R=128):
+    h, w = img.shape
+    out = np.empty(w * h, np.uint8)
+    sau.binarise_sauvola(np.ascontiguousarray(img).reshape(-1), out, w, h, ww, wh, k, R)
+    return out.reshape(h, w) == 0
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+def test_sauvola_oracle_vs_reference_cython(orc, refmods, shape):
+    sau, _ = refmods
+    rng = np.random.default_rng(hash(shape) % 1000)
+    h, w = shape
+    for img in _images(rng, h, w):
+        for ww, k in [(3, 0.34), (33, 0.34), (51, 0.1), (101, 0.34), (151, 0.2), (255, 0.34)]:
+            assert np.array_equal(orc.sauvola(img, ww, k=k), _ref_sauvola(sau, img, ww, ww, k))
+    img = np.clip(rng.normal(150, 60, (h, w)), 0, 255).astype(np.uint8)
+    for ww, wh, k in [(33, 51, 0.34), (51, 33, 0.2), (4, 6, 0.34), (33, 33, -0.2)]:
+        assert np.array_equal(orc.sauvola(img, ww, wh, k=k), _ref_sauvola(sau, img, ww, wh, k))
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (4, 4), (5, 5), (6, 9), (50, 70), (131, 97)])
+def test_denoise_oracle_vs_reference_cython(orc, refmods, shape):
+    _, opt = refmods
+    rng = np.random.default_rng(7)
+    h, w = shape
+    masks = [rng.random((h, w)) < d for d in (0.05, 0.3, 0.6, 0.95)]
+    masks.append(np.eye(h, w, dtype=bool) | np.eye(h, w, 1, dtype=bool))          # thin diagonal: long cascade
+    masks.append(np.ones((h, w), bool)); masks.append(np.zeros((h, w), bool))
+    for m in masks:
+        b = m.copy().view(np.uint8)
+        opt.fast_mask_denoise(b, w, h, 4, 2)
+        assert np.array_equal(orc.denoise(m).view(np.uint8), b)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (2, 3), (5, 5), (30, 41), (64, 120), (91, 57)])
+def test_optimise_oracle_vs_reference_cython(orc, refmods, shape):
+    _, opt = refmods
+    rng = np.random.default_rng(11)
+    h, w = shape
+    for dens in (0.0, 0.05, 0.5, 0.95, 1.0):
+        m = (rng.random((h, w)) < dens).view(np.uint8)
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        c = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for n in (1, 3, 10, 16):
+            for fn in (opt.optimise_gray2, opt.optimise_gray):
+                assert np.array_equal(orc.optimise(m, g, n), fn(m, g, w, h, n))
+            for fn in (opt.optimise_rgb2, opt.optimise_rgb):
+                assert np.array_equal(orc.optimise(m, c, n), fn(m, c, w, h, n))
+
+
+def test_gray_oracle_vs_pillow_all_colours(orc):
+    from PIL import Image
+    allc = np.stack(np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij'), -1)
+    allc = allc.reshape(4096, 4096, 3).astype(np.uint8)
+    assert np.array_equal(orc.rgb2gray(allc), np.array(Image.fromarray(allc).convert('L')))
+
+
+def test_blur_oracle_vs_scipy(orc):
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    for (h, w) in [(1, 1), (3, 2), (5, 9), (60, 80), (151, 130)]:
+        for sig in [0.11, 0.13, 0.2, 0.35, 0.5, 0.9, 1.2, 2.0, 3.3, 6.1]:
+            f = rng.integers(0, 256, (h, w)).astype(np.float32)
+            assert np.array_equal(orc.gauss_blur(f, sig), ndimage.gaussian_filter(f, sigma=sig)), (h, w, sig)
+
+
+def test_thumbnail_oracle_vs_pillow(orc):
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    for (h, w) in [(33, 25), (100, 77), (330, 255), (64, 64), (7, 5), (600, 450)]:
+        for f in [2, 3, 4, 5, 6, 8, 1.5, 2.5]:
+            for ch in (1, 3):
+                img = rng.integers(0, 256, (h, w, 3) if ch == 3 else (h, w), dtype=np.uint8)
+                wd, hd = int(w / f), int(h / f)
+                if wd <= 0 or hd <= 0:
+                    continue
+                im = Image.fromarray(img)
+                im.thumbnail((wd, hd))
+                assert np.array_equal(orc.thumbnail(img, wd, hd), np.array(im)), (h, w, f, ch)
+
+
+@pytest.mark.parametrize('name', golden_cases())
+def test_oracle_vs_golden_reference_outputs(orc, synth, name):
+    g = load_golden(name, synth)
+    page = g['page']
+    gray = page if page.ndim == 2 else orc.rgb2gray(page)
+    assert np.array_equal(orc.threshold_image(gray, 132), g['t33'])
+    assert np.array_equal(orc.threshold_image(gray, g['dpi'], 0.1), g['t01'])
+    assert abs(orc.estimate_noise(gray) - g['sigma']) == 0.0
+    res = orc.decompose(page, dpi=g['dpi'], bg_downsample=g['bg_downsample'], fg_downsample=g['fg_downsample'],
+                        denoise_mask=g['denoise'])
+    assert np.array_equal(res['mask'], g['mask'])
+    assert np.array_equal(res['fg'], g['fg'])
+    assert np.array_equal(res['bg'], g['bg'])
+
+
+def test_ref_pipeline_glue_vs_golden(refmods, synth):
+    from oracle import ref_pipeline as rp
+    for name in golden_cases():
+        g = load_golden(name, synth)
+        res = rp.ref_decompose(g['page'], dpi=g['dpi'], bg_downsample=g['bg_downsample'],
+                               fg_downsample=g['fg_downsample'], denoise_mask=g['denoise'])
+        assert np.array_equal(res['mask'], g['mask']) and np.array_equal(res['fg'], g['fg']) and np.array_equal(res['bg'], g['bg'])
+
+
+def test_invalid_denoise_option_raises(orc):
+    with pytest.raises(ValueError):
+        orc.decompose(np.zeros((8, 8), np.uint8), denoise_mask=None)         # mrc.py:396 (None != 'none')
+
+
+def test_too_small_to_downsample(orc):
+    res = orc.decompose(np.full((2, 9), 200, np.uint8), dpi=100, bg_downsample=3, denoise_mask='none', sigma_est=0.0)
+    assert 'too-small-to-downsample' in res['errors'] and res['bg'].shape == (2, 9)
