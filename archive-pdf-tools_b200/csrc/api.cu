@@ -65,11 +65,11 @@ DecomposeLayout decompose_layout(const b200mrc_decompose_args *a)
     const bool mask_only = (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) != 0;
     L.gray_pitch = align_up((size_t)W, 16); L.gray_page = L.gray_pitch * H;
     L.full_pitch = align_up((size_t)W * C, 16); L.full_page = L.full_pitch * H;
-    Carver c(nullptr, 0);
-    L.off_sigma = (size_t)((uint8_t *)c.take<double>(N) - (uint8_t *)nullptr);
-    L.off_gray = (size_t)((uint8_t *)c.take<uint8_t>(L.gray_page * N) - (uint8_t *)nullptr);
-    if (!mask_only && a->fg_plan) L.off_fgfull = (size_t)((uint8_t *)c.take<uint8_t>(L.full_page * N) - (uint8_t *)nullptr);
-    if (!mask_only && a->bg_plan) L.off_bgfull = (size_t)((uint8_t *)c.take<uint8_t>(L.full_page * N) - (uint8_t *)nullptr);
+    Carver c;
+    L.off_sigma = c.take<double>(N);
+    L.off_gray = c.take<uint8_t>(L.gray_page * N);
+    if (!mask_only && a->fg_plan) L.off_fgfull = c.take<uint8_t>(L.full_page * N);
+    if (!mask_only && a->bg_plan) L.off_bgfull = c.take<uint8_t>(L.full_page * N);
     // stages run one after another on the stream: they share one scratch region
     size_t s = noise_workspace_bytes(W, H, N);
     if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) s = std::max(s, denoise_workspace_bytes(W, H, N));
@@ -79,7 +79,7 @@ DecomposeLayout decompose_layout(const b200mrc_decompose_args *a)
         if (a->bg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->bg_plan, N));
     }
     L.scratch_bytes = s;
-    L.off_scratch = (size_t)((uint8_t *)c.take<uint8_t>(s) - (uint8_t *)nullptr);
+    L.off_scratch = c.take<uint8_t>(s);
     L.total = c.used();
     return L;
 }

@@ -38,18 +38,13 @@ struct DevInfo {
 };
 const DevInfo &dev_info();
 
-// Bump allocator over a caller-provided workspace.
+// Bump allocator of byte offsets inside a caller-provided workspace (256-byte aligned).
 struct Carver {
-    uint8_t *base;
-    size_t off, cap;
-    bool ok;
-    Carver(void *p, size_t bytes) : base((uint8_t *)p), off(0), cap(bytes), ok(true) {}
-    template <typename T> T *take(size_t count) {
+    size_t off = 0;
+    template <typename T> size_t take(size_t count) {
         off = align_up(off, 256);
-        size_t bytes = count * sizeof(T);
-        T *r = (T *)(base ? base + off : nullptr);
-        off += bytes;
-        if (base && off > cap) ok = false;
+        const size_t r = off;
+        off += count * sizeof(T);
         return r;
     }
     size_t used() const { return align_up(off, 256); }

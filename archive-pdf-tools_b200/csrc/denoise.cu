@@ -264,12 +264,12 @@ DenoiseLayout denoise_layout(int W, int H, int N)
     L.Ww = cdiv(W, 32);
     L.tiles_x = cdiv(L.Ww, TWW);
     L.tiles_y = cdiv(H, TR);
-    Carver c(nullptr, 0);
+    Carver c;
     const size_t words = (size_t)H * L.Ww * N;
-    L.off_Mb = (size_t)((uint8_t *)c.take<uint32_t>(words) - (uint8_t *)nullptr);
-    L.off_Rb = (size_t)((uint8_t *)c.take<uint32_t>(words) - (uint8_t *)nullptr);
-    L.off_flags = (size_t)((uint8_t *)c.take<uint8_t>(2 * (size_t)L.tiles_x * L.tiles_y * N) - (uint8_t *)nullptr);
-    L.off_sync = (size_t)((uint8_t *)c.take<unsigned>(8) - (uint8_t *)nullptr);
+    L.off_Mb = c.take<uint32_t>(words);
+    L.off_Rb = c.take<uint32_t>(words);
+    L.off_flags = c.take<uint8_t>(2 * (size_t)L.tiles_x * L.tiles_y * N);
+    L.off_sync = c.take<unsigned>(8);
     L.total = c.used();
     return L;
 }

@@ -282,11 +282,11 @@ OptLayout opt_layout(int W, int H, int N)
 {
     // sized for the worst case strip count (narrowest strips)
     const size_t Smax = (size_t)cdiv(W, 32);
-    Carver c(nullptr, 0);
+    Carver c;
     OptLayout L;
-    L.off_mailbox = (size_t)((uint8_t *)c.take<uint32_t>((size_t)N * Smax * H * 2 * OH) - (uint8_t *)nullptr);
-    L.off_prog = (size_t)((uint8_t *)c.take<int>((size_t)N * Smax) - (uint8_t *)nullptr);
-    L.off_ticket = (size_t)((uint8_t *)c.take<unsigned>(4) - (uint8_t *)nullptr);
+    L.off_mailbox = c.take<uint32_t>((size_t)N * Smax * H * 2 * OH);
+    L.off_prog = c.take<int>((size_t)N * Smax);
+    L.off_ticket = c.take<unsigned>(4);
     L.total = c.used();
     return L;
 }
