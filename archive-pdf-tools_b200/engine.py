@@ -63,7 +63,11 @@ class Plane:
 
     def upload(self, host, non_blocking=True):
         """host: uint8/bool ndarray or CPU tensor [N,H,W] / [N,H,W,C] (pinned for async copies)."""
-        ht = host if isinstance(host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(host).view(np.uint8))
+        if not isinstance(host, torch.Tensor):
+            host = np.ascontiguousarray(host).view(np.uint8)
+            if not host.flags.writeable:
+                host = host.copy()
+        ht = host if isinstance(host, torch.Tensor) else torch.from_numpy(host)
         ht = ht.reshape(self.n, self.h, self.w * self.c)
         if self.pitch == self.w * self.c:
             self.t.copy_(ht, non_blocking=non_blocking)
@@ -269,4 +273,46 @@ class DecomposeBatch:
         if self._args is None or self._args[0] != key:
             self._args = (key, self._build_args(window, k, R, denoise_mask == DENOISE_FAST, sigma is not None))
         L.check(L.lib().b200mrc_decompose(C.byref(self._args[1]), _stream_ptr()), 'b200mrc_decompose')
+        return self
+
+    # stage-by-stage form of run(): the same kernels through the per-stage C-ABI entry points, with a
+    # CUDA event recorded between stages so a profile of the step comes from the step itself
+    STAGES = ('noise', 'gray_blur', 'sauvola', 'denoise', 'optimise', 'fg_thumbnail', 'bg_thumbnail')
+
+    def run_staged(self, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST, sigma=None, events=None):
+        """events: None or a dict filled with stage -> (start_event, end_event)."""
+        eng = self.eng
+        if getattr(self, '_gray', None) is None:
+            self._gray = Plane(self.n, self.h, self.w, 1, eng.device)
+            self._fg_full = Plane(self.n, self.h, self.w, self.c, eng.device) if (self.fg_plan and not self.mask_only) else None
+            self._bg_full = Plane(self.n, self.h, self.w, self.c, eng.device) if (self.bg_plan and not self.mask_only) else None
+
+        def stage(name, fn):
+            if events is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            events[name] = (a, b)
+
+        if sigma is None:
+            def _noise():
+                self.sigma = eng.estimate_noise(self.img)
+            stage('noise', _noise)
+            sig = self.sigma
+        else:
+            self.sigma_in.copy_(torch.as_tensor(np.asarray(sigma, np.float64)))
+            sig = self.sigma_in
+        stage('gray_blur', lambda: eng.gray_blur(self.img, self._gray, sig))
+        stage('sauvola', lambda: eng.sauvola(self._gray, self.mask, window, window, k, R))
+        if denoise_mask == DENOISE_FAST:
+            stage('denoise', lambda: eng.denoise(self.mask, 4, 2))
+        if self.mask_only:
+            return self
+        fgf = self._fg_full if self.fg_plan else self.fg
+        bgf = self._bg_full if self.bg_plan else self.bg
+        stage('optimise', lambda: eng.optimise(self.mask, self.img, fgf, 3, bgf, 10))
+        if self.fg_plan:
+            stage('fg_thumbnail', lambda: eng.resample(self.fg_plan, fgf, self.fg))
+        if self.bg_plan:
+            stage('bg_thumbnail', lambda: eng.resample(self.bg_plan, bgf, self.bg))
         return self
