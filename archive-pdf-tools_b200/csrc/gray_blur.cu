@@ -58,88 +58,138 @@ __device__ double np_sum(const double *a, int n)
     return res;
 }
 
-template <int RLO, int RHI, int TH, int TW>
-__global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
+// One tile of one page.  256 threads as 32 x 8: no integer division in the loops.
+template <int RHI, int TH, int TW>
+__device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t *in, uint8_t *out, int x0, int y0,
+                                          int radius, const double *sw, float *stmp, uint8_t *sg)
 {
-    constexpr int GW = TW + 2 * RHI;           // smem row length (u8 tile and f32 tile)
-    constexpr int GH = TH + 2 * RHI;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    double *sw = reinterpret_cast<double *>(smem_raw);                    // RHI+1 weights
-    double *sphi = sw + (RHI + 1);                                        // 2*RHI+1 scratch
-    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));        // TH x GW
-    uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);            // GH x GW
-
-    const int page = blockIdx.z;
-    double sig_est = p.sigma ? p.sigma[page] : 0.0;
-    int radius = 0;
-    double sigma = 0.0;
-    if (sig_est > 1.0) {                       // NaN compares false: no blur
-        sigma = sig_est * 0.1;
-        const double rr = 4.0 * sigma + 0.5;
-        radius = rr > 1.0e6 ? 1000000 : (int)rr;
-    }
-    if (radius > 128) {                        // outside every configuration: flag once
-        if (RLO > 0 && p.err && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) atomicExch(p.err, 1);
-        return;
-    }
-    if (radius < RLO || radius > RHI) return;
-
-    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
-    uint8_t *out = p.out + (int64_t)page * p.out_stride;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    if (x0 >= p.W || y0 >= p.H) return;
-    const int tid = threadIdx.x;
-
-    if (radius == 0) {
-        for (int idx = tid; idx < TH * TW; idx += 256) {
-            const int y = y0 + idx / TW, x = x0 + idx % TW;
-            if (y < p.H && x < p.W) out[(int64_t)y * p.out_pitch + x] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+    constexpr int GW = TW + 2 * RHI;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gw = TW + 2 * radius, gh = TH + 2 * radius;
+    for (int ly = ty; ly < gh; ly += 8) {
+        const int y = reflect_idx(y0 - radius + ly, p.H);
+        for (int lx = tx; lx < gw; lx += 32) {
+            const int x = reflect_idx(x0 - radius + lx, p.W);
+            sg[ly * GW + lx] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
         }
-        return;
     }
+    __syncthreads();
+    // axis 0 (vertical), for every column incl. the horizontal halo
+    for (int ly = ty; ly < TH; ly += 8)
+        for (int lx = tx; lx < gw; lx += 32) {
+            const uint8_t *c = sg + (ly + radius) * GW + lx;
+            double acc = __dmul_rn((double)c[0], sw[0]);
+            for (int j = radius; j >= 1; j--)
+                acc = __dadd_rn(acc, __dmul_rn((double)((int)c[-j * GW] + (int)c[j * GW]), sw[j]));
+            stmp[ly * GW + lx] = __double2float_rn(acc);
+        }
+    __syncthreads();
+    // axis 1 (horizontal) + uint8 truncation
+    for (int ly = ty; ly < TH; ly += 8) {
+        const int y = y0 + ly;
+        if (y >= p.H) break;
+        for (int lx = tx; lx < TW; lx += 32) {
+            const int x = x0 + lx;
+            if (x >= p.W) break;
+            const float *c = stmp + ly * GW + lx + radius;
+            double acc = __dmul_rn((double)c[0], sw[0]);
+            for (int j = radius; j >= 1; j--)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)c[-j], (double)c[j]), sw[j]));
+            const float f = __double2float_rn(acc);
+            out[(int64_t)y * p.out_pitch + x] = (uint8_t)(int)f;          // astype(uint8): truncation
+        }
+    }
+}
 
-    // weights (scipy _gaussian_kernel1d), double; thread-serial so the summation order is fixed
-    if (tid <= 2 * radius) {
-        const int j = tid - radius;
+__device__ __forceinline__ int page_radius(const GrayBlurParams &p, int page, double &sigma)
+{
+    const double sig_est = p.sigma ? p.sigma[page] : 0.0;
+    sigma = 0.0;
+    if (!(sig_est > 1.0)) return 0;            // NaN compares false: no blur
+    sigma = sig_est * 0.1;
+    const double rr = 4.0 * sigma + 0.5;
+    return rr > 1.0e6 ? 1000000 : (int)rr;
+}
+
+__device__ __forceinline__ void blur_weights(int radius, double sigma, double *sw, double *sphi)
+{
+    // weights (scipy _gaussian_kernel1d), double; thread-serial sum so the summation order is fixed
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= 2 * radius; i += 256) {
+        const int j = i - radius;
         const double sigma2 = sigma * sigma;
-        sphi[tid] = exp(__dmul_rn(-0.5 / sigma2, (double)(j * j)));
+        sphi[i] = exp(__dmul_rn(-0.5 / sigma2, (double)(j * j)));
     }
     __syncthreads();
     if (tid == 0) {
         const double sum = np_sum(sphi, 2 * radius + 1);
         for (int j = 0; j <= radius; j++) sw[j] = sphi[radius + j] / sum;
     }
-
-    const int gw = TW + 2 * radius, gh = TH + 2 * radius;
-    for (int idx = tid; idx < gh * gw; idx += 256) {
-        const int ly = idx / gw, lx = idx % gw;
-        const int y = reflect_idx(y0 - radius + ly, p.H), x = reflect_idx(x0 - radius + lx, p.W);
-        sg[ly * GW + lx] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
-    }
     __syncthreads();
+}
 
-    // axis 0 (vertical), for every column incl. the horizontal halo
-    for (int idx = tid; idx < TH * gw; idx += 256) {
-        const int ly = idx / gw, lx = idx % gw;
-        const uint8_t *c = sg + (ly + radius) * GW + lx;
-        double acc = __dmul_rn((double)c[0], sw[0]);
-        for (int j = radius; j >= 1; j--)
-            acc = __dadd_rn(acc, __dmul_rn((double)((int)c[-j * GW] + (int)c[j * GW]), sw[j]));
-        stmp[ly * GW + lx] = __double2float_rn(acc);
+// Small-radius configuration (0..RHI): one CTA per tile, grid over (tiles, pages).
+template <int RHI, int TH, int TW>
+__global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
+{
+    constexpr int GW = TW + 2 * RHI;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    double *sw = reinterpret_cast<double *>(smem_raw);                    // RHI+1 weights
+    double *sphi = sw + (RHI + 1);                                        // 2*RHI+1 scratch
+    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));        // TH x GW
+    uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);            // (TH + 2 RHI) x GW
+
+    const int page = blockIdx.z;
+    double sigma;
+    const int radius = page_radius(p, page, sigma);
+    if (radius > RHI) return;                  // the large-radius kernel owns this page
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (radius == 0) {
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        for (int ly = ty; ly < TH; ly += 8) {
+            const int y = y0 + ly;
+            if (y >= p.H) break;
+            for (int lx = tx; lx < TW; lx += 32) {
+                const int x = x0 + lx;
+                if (x < p.W) out[(int64_t)y * p.out_pitch + x] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+            }
+        }
+        return;
     }
-    __syncthreads();
+    blur_weights(radius, sigma, sw, sphi);
+    blur_tile<RHI, TH, TW>(p, in, out, x0, y0, radius, sw, stmp, sg);
+}
 
-    // axis 1 (horizontal) + uint8 truncation
-    for (int idx = tid; idx < TH * TW; idx += 256) {
-        const int ly = idx / TW, lx = idx % TW;
-        const int y = y0 + ly, x = x0 + lx;
-        if (y >= p.H || x >= p.W) continue;
-        const float *c = stmp + ly * GW + lx + radius;
-        double acc = __dmul_rn((double)c[0], sw[0]);
-        for (int j = radius; j >= 1; j--)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)c[-j], (double)c[j]), sw[j]));
-        const float f = __double2float_rn(acc);
-        out[(int64_t)y * p.out_pitch + x] = (uint8_t)(int)f;          // astype(uint8): truncation
+// Large-radius configuration (RLO..RHI): persistent CTAs walk the pages, skip those the small
+// kernel handled, and share the tiles of the rest -- no grid of a million early-exit CTAs.
+template <int RLO, int RHI, int TH, int TW>
+__global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p, int n_pages)
+{
+    constexpr int GW = TW + 2 * RHI;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    double *sw = reinterpret_cast<double *>(smem_raw);
+    double *sphi = sw + (RHI + 1);
+    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));
+    uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);
+    const int tiles_x = (p.W + TW - 1) / TW, tiles_y = (p.H + TH - 1) / TH;
+    for (int page = 0; page < n_pages; page++) {
+        double sigma;
+        const int radius = page_radius(p, page, sigma);
+        if (radius < RLO) continue;
+        if (radius > RHI) {
+            if (p.err && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.err, 1);
+            continue;
+        }
+        __syncthreads();
+        blur_weights(radius, sigma, sw, sphi);
+        const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+        uint8_t *out = p.out + (int64_t)page * p.out_stride;
+        for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+            __syncthreads();
+            blur_tile<RHI, TH, TW>(p, in, out, (t % tiles_x) * TW, (t / tiles_x) * TH, radius, sw, stmp, sg);
+        }
     }
 }
 
@@ -160,25 +210,19 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
     {
         constexpr int TH = 32, TW = 128, RHI = 16;
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<0, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
-        k_gray_blur<0, RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        k_gray_blur<RHI, TH, TW><<<grid, 256, smem, st>>>(p);
         B200MRC_LAUNCH_CHECK();
     }
     if (sigma) {
         constexpr int TH = 16, TW = 32, RHI = 128;
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<17, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
-        k_gray_blur<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<17, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = cdiv(W, TW) * cdiv(H, TH);
+        int grid = dev_info().sm_count * 2;
+        if (grid > tiles) grid = tiles;
+        k_gray_blur_large<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N);
         B200MRC_LAUNCH_CHECK();
     }
     return B200MRC_OK;

@@ -293,6 +293,12 @@ OptLayout opt_layout(int W, int H, int N)
 
 }  // namespace
 
+int launch_optimise_fast(const uint8_t *mask, int64_t mpitch, int64_t mstride,
+                         const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
+                         uint8_t *obg, int64_t bpitch, int64_t bstride,
+                         int W, int H, int N, uint32_t *mailbox, int *prog, unsigned *ticket, cudaStream_t st);
+
 size_t optimise_workspace_bytes(int W, int H, int N) { return opt_layout(W, H, N).total; }
 
 int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
@@ -303,10 +309,17 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
 {
     const OptLayout L = opt_layout(W, H, N);
     if (!workspace || workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
+    uint8_t *ws = (uint8_t *)workspace;
+    if (nfg == 3 && nbg == 10) {
+        // production path (TMA-fed, specialised for the reference's n); falls through when it does not apply
+        const int frc = launch_optimise_fast(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
+                                             obg, bpitch, bstride, W, H, N, (uint32_t *)(ws + L.off_mailbox),
+                                             (int *)(ws + L.off_prog), (unsigned *)(ws + L.off_ticket), st);
+        if (frc != B200MRC_ERR_UNSUPPORTED) return frc;
+    }
     OptPlan plan;
     int rc = plan_optimise(W, N, nfg, nbg, plan);
     if (rc != B200MRC_OK) return rc;
-    uint8_t *ws = (uint8_t *)workspace;
     OptParams p;
     p.mask = mask; p.mpitch = mpitch; p.mstride = mstride;
     p.img = img; p.ipitch = ipitch; p.istride = istride; p.C = C;

@@ -96,33 +96,68 @@ __device__ __forceinline__ uint8_t clip8(int v)
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// out[y][xx][c] = clip8(2^21 + sum_k in[y][xmin+k][c] * kk[xx][k]); one thread per output byte
-__global__ void __launch_bounds__(256) k_resample_h(const ResampleParams p)
+// out[y][xx][c] = clip8(2^21 + sum_k in[y][xmin+k][c] * kk[xx][k]).  One thread per output PIXEL
+// (all channels share the coefficient fetch and the address arithmetic) and RPT consecutive rows
+// (the coefficient window is loaded once per thread).
+constexpr int H_RPT = 4;
+template <int C>
+__global__ void __launch_bounds__(128) k_resample_h(const ResampleParams p)
 {
-    const int b = blockIdx.x * 256 + threadIdx.x;            // byte within the output row
-    const int y = blockIdx.y, page = blockIdx.z;
-    if (b >= p.out_w * p.C) return;
-    const int xx = b / p.C, c = b - xx * p.C;
+    const int xx = blockIdx.x * 128 + threadIdx.x;
+    const int y0 = blockIdx.y * H_RPT, page = blockIdx.z;
+    if (xx >= p.out_w) return;
     const int xmin = p.bounds[2 * xx], cnt = p.bounds[2 * xx + 1];
     const int *k = p.kk + (size_t)xx * p.ksize;
-    const uint8_t *src = p.in + (int64_t)page * p.in_stride + (int64_t)y * p.in_pitch + (int64_t)xmin * p.C + c;
-    int ss = 1 << 21;
-    for (int i = 0; i < cnt; i++) ss += (int)src[(int64_t)i * p.C] * k[i];
-    p.out[(int64_t)page * p.out_stride + (int64_t)y * p.out_pitch + b] = clip8(ss);
+    const uint8_t *src = p.in + (int64_t)page * p.in_stride + (int64_t)y0 * p.in_pitch + (int64_t)xmin * C;
+    uint8_t *dst = p.out + (int64_t)page * p.out_stride + (int64_t)y0 * p.out_pitch + (int64_t)xx * C;
+    const int rows = min(H_RPT, p.in_h - y0);
+    int acc[H_RPT][C];
+#pragma unroll
+    for (int r = 0; r < H_RPT; r++)
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[r][c] = 1 << 21;
+    for (int i = 0; i < cnt; i++) {
+        const int kv = __ldg(k + i);
+#pragma unroll
+        for (int r = 0; r < H_RPT; r++) {
+            if (r < rows) {
+                const uint8_t *q = src + (int64_t)r * p.in_pitch + i * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[r][c] += (int)q[c] * kv;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < H_RPT; r++)
+        if (r < rows) {
+#pragma unroll
+            for (int c = 0; c < C; c++) dst[(int64_t)r * p.out_pitch + c] = clip8(acc[r][c]);
+        }
 }
 
-// out[yy][b] = clip8(2^21 + sum_k in[ymin+k][b] * kk[yy][k])
+// out[yy][b] = clip8(2^21 + sum_k in[ymin+k][b] * kk[yy][k]); one thread per 4 consecutive bytes
+// (rows of both planes are 16-byte aligned workspace / pitched planes)
 __global__ void __launch_bounds__(256) k_resample_v(const ResampleParams p)
 {
-    const int b = blockIdx.x * 256 + threadIdx.x;
+    const int b4 = (blockIdx.x * 256 + threadIdx.x) * 4;
     const int yy = blockIdx.y, page = blockIdx.z;
-    if (b >= p.out_w * p.C) return;
+    const int nb = p.out_w * p.C;
+    if (b4 >= nb) return;
     const int ymin = p.bounds[2 * yy], cnt = p.bounds[2 * yy + 1];
     const int *k = p.kk + (size_t)yy * p.ksize;
-    const uint8_t *src = p.in + (int64_t)page * p.in_stride + (int64_t)ymin * p.in_pitch + b;
-    int ss = 1 << 21;
-    for (int i = 0; i < cnt; i++) ss += (int)src[(int64_t)i * p.in_pitch] * k[i];
-    p.out[(int64_t)page * p.out_stride + (int64_t)yy * p.out_pitch + b] = clip8(ss);
+    const uint8_t *src = p.in + (int64_t)page * p.in_stride + (int64_t)ymin * p.in_pitch + b4;
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21, s3 = 1 << 21;
+    for (int i = 0; i < cnt; i++) {
+        const int kv = __ldg(k + i);
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(src + (int64_t)i * p.in_pitch);
+        s0 += (int)(w & 0xffu) * kv; s1 += (int)((w >> 8) & 0xffu) * kv;
+        s2 += (int)((w >> 16) & 0xffu) * kv; s3 += (int)(w >> 24) * kv;
+    }
+    uint8_t *dst = p.out + (int64_t)page * p.out_stride + (int64_t)yy * p.out_pitch + b4;
+    const uint32_t o = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16) | ((uint32_t)clip8(s3) << 24);
+    if (b4 + 3 < nb && (((uintptr_t)dst) & 3) == 0) *reinterpret_cast<uint32_t *>(dst) = o;
+    else
+        for (int j = 0; j < 4 && b4 + j < nb; j++) dst[j] = (uint8_t)(o >> (8 * j));
 }
 
 struct ReduceParams {
@@ -270,7 +305,7 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
                                 void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!pl || !in || !out || n_pages <= 0) return B200MRC_ERR_INVALID;
-    if (n_pages > 65535 || pl->SH > 65535 || pl->OH > 65535) return B200MRC_ERR_UNSUPPORTED;
+    if (n_pages > 65535 || pl->SH > 65535 * H_RPT || pl->OH > 65535) return B200MRC_ERR_UNSUPPORTED;
     if (workspace_bytes < b200mrc_resample_workspace_bytes(pl, n_pages) || (!workspace && workspace_bytes)) return B200MRC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)workspace;
@@ -302,8 +337,9 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         else { h.out = out; h.out_pitch = out_pitch; h.out_stride = out_page_stride; }
         h.C = pl->C; h.in_w = pl->SW; h.in_h = pl->SH; h.out_w = pl->OW; h.out_h = pl->SH; h.ksize = pl->ksize_h;
         h.bounds = pl->d_bounds_h; h.kk = pl->d_kk_h;
-        dim3 grid(cdiv(pl->OW * pl->C, 256), pl->SH, n_pages);
-        k_resample_h<<<grid, 256, 0, st>>>(h);
+        dim3 grid(cdiv(pl->OW, 128), cdiv(pl->SH, H_RPT), n_pages);
+        if (pl->C == 1) k_resample_h<1><<<grid, 128, 0, st>>>(h);
+        else k_resample_h<3><<<grid, 128, 0, st>>>(h);
         B200MRC_LAUNCH_CHECK();
         src = h.out; src_pitch = h.out_pitch; src_stride = h.out_stride;
     }
@@ -313,7 +349,8 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         v.out = out; v.out_pitch = out_pitch; v.out_stride = out_page_stride;
         v.C = pl->C; v.in_w = pl->OW; v.in_h = pl->SH; v.out_w = pl->OW; v.out_h = pl->OH; v.ksize = pl->ksize_v;
         v.bounds = pl->d_bounds_v; v.kk = pl->d_kk_v;
-        dim3 grid(cdiv(pl->OW * pl->C, 256), pl->OH, n_pages);
+        if ((src_pitch & 3) || (src_stride & 3) || ((uintptr_t)src & 3)) return B200MRC_ERR_ALIGNMENT;
+        dim3 grid(cdiv(cdiv(pl->OW * pl->C, 4), 256), pl->OH, n_pages);
         k_resample_v<<<grid, 256, 0, st>>>(v);
         B200MRC_LAUNCH_CHECK();
     }

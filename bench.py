@@ -69,9 +69,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
         self.proc.terminate()
@@ -80,7 +83,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.12):
+                continue
             f = [x.strip() for x in r.split(',')]
             if len(f) < 7:
                 continue
@@ -141,7 +146,8 @@ def run_reference(args, rank):
         return 0
     pool, cores, kind = cpu_pool()
     cpu_step(pool, cores, kind)                       # pool start-up + imports, untimed
-    for _ in range(max(0, args.warmup - 1)):
+    args.steps = min(args.steps, 5)                   # bounded CPU sample: the run must end within minutes
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
         cpu_step(pool, cores, kind)
     t0 = time.time()
     npages = 0
@@ -170,7 +176,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -216,15 +222,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident steps (inputs in HBM, 1.6 GB per batch >> 126 MB L2: no flush needed)
-    for _ in range(args.warmup):
-        batch.run_staged(WINDOW, denoise_mask='fast')
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                              # nvidia-smi needs a moment to start: begin before the warm-up
+    for _ in range(args.warmup):
+        batch.run_staged(WINDOW, denoise_mask='fast')
+    torch.cuda.synchronize()
+    t_w = time.time()
+    while rank == 0 and sampler.proc and not sampler.rows and time.time() - t_w < 3.0:
+        batch.run_staged(WINDOW, denoise_mask='fast')   # extra untimed warm-up until the sampler is alive
+        torch.cuda.synchronize()
+    barrier()
     launches0 = _lib.lib().b200mrc_launch_count()
     stage_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts0 = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         ev = {}
@@ -232,8 +244,9 @@ def main():
         stage_events.append(ev)
     e1.record()
     barrier()
+    ts1 = sampler.mark()
     launches = _lib.lib().b200mrc_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(ts0, ts1) if rank == 0 else None
     dev_ms = e0.elapsed_time(e1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device='cuda')
     if world > 1:
