@@ -28,6 +28,8 @@
 //     always waits on a CTA that is already resident (no deadlock, any grid size).
 // Algorithmic HBM bytes per pixel (RGB): 3 (img) + 1 (mask) read, 3 (fg) + 3 (bg) written.
 #include "common.cuh"
+#include <cstring>
+#include <cstdlib>
 
 namespace b200mrc {
 namespace {
@@ -276,7 +278,7 @@ int plan_optimise(int W, int N, int nfg, int nbg, OptPlan &best)
     return B200MRC_OK;
 }
 
-struct OptLayout { size_t off_mailbox, off_prog, off_ticket, total; };
+struct OptLayout { size_t off_mailbox, off_prog, off_ticket, off_rec, total; };
 
 OptLayout opt_layout(int W, int H, int N)
 {
@@ -287,6 +289,7 @@ OptLayout opt_layout(int W, int H, int N)
     L.off_mailbox = c.take<uint32_t>((size_t)N * Smax * H * 2 * OH);
     L.off_prog = c.take<int>((size_t)N * Smax);
     L.off_ticket = c.take<unsigned>(4);
+    L.off_rec = c.take<uint8_t>(align_up((size_t)W * 8, 16) * (size_t)H * (size_t)N);   // FIR record plane (optimise_split.cu)
     L.total = c.used();
     return L;
 }
@@ -299,6 +302,12 @@ int launch_optimise_fast(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                          uint8_t *obg, int64_t bpitch, int64_t bstride,
                          int W, int H, int N, uint32_t *mailbox, int *prog, unsigned *ticket, cudaStream_t st);
 
+int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
+                          const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                          uint8_t *ofg, int64_t fpitch, int64_t fstride,
+                          uint8_t *obg, int64_t bpitch, int64_t bstride,
+                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, int *prog, unsigned *ticket, cudaStream_t st);
+
 size_t optimise_workspace_bytes(int W, int H, int N) { return opt_layout(W, H, N).total; }
 
 int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
@@ -310,8 +319,16 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     const OptLayout L = opt_layout(W, H, N);
     if (!workspace || workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
     uint8_t *ws = (uint8_t *)workspace;
-    if (nfg == 3 && nbg == 10) {
-        // production path (TMA-fed, specialised for the reference's n); falls through when it does not apply
+    const char *path = getenv("B200MRC_OPT_PATH");          // "split" (default) | "fused" | "generic": A/B switch for profiling
+    if (nfg == 3 && nbg == 10 && (!path || !strcmp(path, "split"))) {
+        // production path: parallel FIR record plane + short sequential IIR sweep (optimise_split.cu)
+        const int frc = launch_optimise_split(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
+                                              obg, bpitch, bstride, W, H, N, ws + L.off_rec, (uint32_t *)(ws + L.off_mailbox),
+                                              (int *)(ws + L.off_prog), (unsigned *)(ws + L.off_ticket), st);
+        if (frc != B200MRC_ERR_UNSUPPORTED) return frc;
+    }
+    if (nfg == 3 && nbg == 10 && (!path || strcmp(path, "generic"))) {
+        // single fused sweep (TMA-fed, specialised for the reference's n); falls through when it does not apply
         const int frc = launch_optimise_fast(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
                                              obg, bpitch, bstride, W, H, N, (uint32_t *)(ws + L.off_mailbox),
                                              (int *)(ws + L.off_prog), (unsigned *)(ws + L.off_ticket), st);
