@@ -22,6 +22,7 @@ struct GrayBlurParams {
     int W, H;
     const double *sigma;     // device, per page, may be null
     int *err;                // device error flag (radius out of range), may be null
+    int rlo;                 // tiled kernel: smallest radius it handles (5 when the fast kernel ran, else 0)
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n)
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
     const int page = blockIdx.z;
     double sigma;
     const int radius = page_radius(p, page, sigma);
-    if (radius > RHI) return;                  // the large-radius kernel owns this page
+    if (radius > RHI || radius < p.rlo) return;   // the large-radius / fast kernel owns this page
     const uint8_t *in = p.in + (int64_t)page * p.in_stride;
     uint8_t *out = p.out + (int64_t)page * p.out_stride;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p,
         const int radius = page_radius(p, page, sigma);
         if (radius < RLO) continue;
         if (radius > RHI) {
-            if (p.err && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.err, 1);
+            if (RHI >= 128 && p.err && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.err, 1);
             continue;
         }
         __syncthreads();
@@ -190,6 +191,115 @@ __global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p,
             __syncthreads();
             blur_tile<RHI, TH, TW>(p, in, out, (t % tiles_x) * TW, (t / tiles_x) * TH, radius, sw, stmp, sg);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path for radius 0..4 (sigma_est < 11.25, i.e. every ordinary scan): a warp marches a
+// 128-px-wide column strip down a band of rows, 4 adjacent pixels per lane.  The (2R+1)-row gray
+// window lives in registers (one u32 = 4 gray bytes per row), the vertical pass needs no
+// communication, the horizontal pass takes its R neighbours from the adjacent lanes by shuffle;
+// lanes 0 and 31 only supply halo.  Loads are 32-bit (3 per 4 RGB pixels), stores one u32.
+constexpr int FB_BAND = 64;            // output rows per warp
+
+template <int C>
+__device__ __forceinline__ uint32_t load_gray4(const GrayBlurParams &p, const uint8_t *in, int y, int x)
+{
+    // 4 gray pixels x..x+3 of row y (x % 4 == 0); columns outside [0, W) are reflected
+    if (x >= 0 && x + 3 < p.W) {
+        const uint8_t *q = in + (int64_t)y * p.in_pitch + (int64_t)x * C;
+        if (C == 1) return *reinterpret_cast<const uint32_t *>(q);
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(q), b = *reinterpret_cast<const uint32_t *>(q + 4),
+                       c = *reinterpret_cast<const uint32_t *>(q + 8);
+        // a = r0 g0 b0 r1 | b = g1 b1 r2 g2 | c = b2 r3 g3 b3
+        const uint32_t g0 = luma_l24(a & 0xff, (a >> 8) & 0xff, (a >> 16) & 0xff);
+        const uint32_t g1 = luma_l24(a >> 24, b & 0xff, (b >> 8) & 0xff);
+        const uint32_t g2 = luma_l24((b >> 16) & 0xff, b >> 24, c & 0xff);
+        const uint32_t g3 = luma_l24((c >> 8) & 0xff, (c >> 16) & 0xff, c >> 24);
+        return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r |= load_gray(in, p.in_pitch, C, y, reflect_idx(x + k, p.W)) << (8 * k);
+    return r;
+}
+
+template <int R, int C>
+__device__ __forceinline__ void blur_march(const GrayBlurParams &p, const uint8_t *in, uint8_t *out,
+                                           int x, int by0, int by1, const double *sw)
+{
+    const int lane = threadIdx.x & 31;
+    double w[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; j++) w[j] = sw[j];
+    uint32_t win[2 * R + 1];                       // gray rows y-R .. y+R (4 px each)
+#pragma unroll
+    for (int j = 0; j < 2 * R; j++) win[j + 1] = load_gray4<C>(p, in, reflect_idx(by0 - R + j, p.H), x);
+    for (int y = by0; y < by1; y++) {
+#pragma unroll
+        for (int j = 0; j < 2 * R; j++) win[j] = win[j + 1];
+        win[2 * R] = load_gray4<C>(p, in, reflect_idx(y + R, p.H), x);
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double acc = __dmul_rn((double)(int)((win[R] >> (8 * k)) & 0xff), w[0]);
+#pragma unroll
+            for (int j = R; j >= 1; j--)
+                acc = __dadd_rn(acc, __dmul_rn((double)(int)(((win[R - j] >> (8 * k)) & 0xff) + ((win[R + j] >> (8 * k)) & 0xff)), w[j]));
+            v[k] = __double2float_rn(acc);
+        }
+        uint32_t o = 0;
+        if (R == 0) {
+            o = win[0];
+        } else {
+            // horizontal neighbours: ext[R + k] = v[k]; ext[0..R) from the left lane, ext[R+4..) from the right lane
+            double ext[4 + 2 * R];
+#pragma unroll
+            for (int k = 0; k < 4; k++) ext[R + k] = (double)v[k];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                ext[j] = (double)__shfl_up_sync(0xffffffffu, v[4 - R + j], 1);
+                ext[R + 4 + j] = (double)__shfl_down_sync(0xffffffffu, v[j], 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                double acc = __dmul_rn(ext[R + k], w[0]);
+#pragma unroll
+                for (int j = R; j >= 1; j--) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ext[R + k - j], ext[R + k + j]), w[j]));
+                o |= ((uint32_t)(int)__double2float_rn(acc) & 0xffu) << (8 * k);      // astype(uint8): truncation
+            }
+        }
+        if (lane >= 1 && lane <= 30 && x < p.W) {
+            uint8_t *q = out + (int64_t)y * p.out_pitch + x;
+            if (x + 3 < p.W) *reinterpret_cast<uint32_t *>(q) = o;
+            else for (int k = 0; k < 4 && x + k < p.W; k++) q[k] = (uint8_t)(o >> (8 * k));
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_gray_blur_fast(const GrayBlurParams p)
+{
+    __shared__ double sw[8];
+    __shared__ double sphi[16];
+    const int page = blockIdx.z;
+    double sigma;
+    const int radius = page_radius(p, page, sigma);
+    if (radius > 4) return;                    // the tiled kernels own this page
+    if (radius > 0) blur_weights(radius, sigma, sw, sphi);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int by0 = (blockIdx.y * 8 + warp) * FB_BAND;
+    if (by0 >= p.H) return;
+    const int by1 = min(p.H, by0 + FB_BAND);
+    const int x = blockIdx.x * 120 - 4 + 4 * lane;
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride;
+    switch (radius) {
+    case 0: blur_march<0, C>(p, in, out, x, by0, by1, sw); break;
+    case 1: blur_march<1, C>(p, in, out, x, by0, by1, sw); break;
+    case 2: blur_march<2, C>(p, in, out, x, by0, by1, sw); break;
+    case 3: blur_march<3, C>(p, in, out, x, by0, by1, sw); break;
+    default: blur_march<4, C>(p, in, out, x, by0, by1, sw); break;
     }
 }
 
@@ -206,13 +316,34 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
                      uint8_t *out, int64_t out_pitch, int64_t out_stride,
                      int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st)
 {
-    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag};
-    {
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0};
+    // fast marching kernel: needs 4-byte aligned rows and an image at least as large as its reflect reach
+    const bool fast_ok = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
+                         !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
+    if (fast_ok) {
+        dim3 grid(cdiv(W, 120), cdiv(cdiv(H, FB_BAND), 8), N);
+        if (C == 1) k_gray_blur_fast<1><<<grid, 256, 0, st>>>(p);
+        else k_gray_blur_fast<3><<<grid, 256, 0, st>>>(p);
+        B200MRC_LAUNCH_CHECK();
+        p.rlo = 5;
+    }
+    if (!fast_ok) {
+        // tiny images: the tiled kernel does everything up to radius 16 (one CTA per tile)
         constexpr int TH = 32, TW = 128, RHI = 16;
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
         B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
         k_gray_blur<RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        B200MRC_LAUNCH_CHECK();
+    } else if (sigma) {
+        // radius 5..16: persistent CTAs walk the pages and share the tiles of those that need it
+        constexpr int TH = 32, TW = 128, RHI = 16;
+        constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<5, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = cdiv(W, TW) * cdiv(H, TH);
+        int grid = dev_info().sm_count * 4;
+        if (grid > tiles) grid = tiles;
+        k_gray_blur_large<5, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N);
         B200MRC_LAUNCH_CHECK();
     }
     if (sigma) {

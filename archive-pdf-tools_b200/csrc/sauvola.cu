@@ -83,6 +83,19 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
     uint32_t cs[SK], cq[SK];
 #pragma unroll
     for (int j = 0; j < SK; j++) { cs[j] = 0; cq[j] = 0; }
+    // row-invariant per-thread constants: smem slots of the two prefix entries of each pixel's window,
+    // the window width, and where this thread publishes its own prefixes
+    int slot_hi[SK], slot_lo[SK], slot_st[SK], nxv[SK];
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+        const int x = gx + j, i = i0 + j;
+        const int chi = i + p.r + 1, clo = max(i - p.l + 1, 0), cst = i + 1;
+        slot_hi[j] = (chi & 3) * (ST + 1) + (chi >> 2);
+        slot_lo[j] = (clo & 3) * (ST + 1) + (clo >> 2);
+        slot_st[j] = (cst & 3) * (ST + 1) + (cst >> 2);
+        nxv[j] = (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0;
+    }
+    const bool nx_uniform = nxv[0] == nxv[1] && nxv[1] == nxv[2] && nxv[2] == nxv[3];
 
     // ---- band warm-up: column sums over the window rows of the first output row
     {
@@ -135,10 +148,7 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
         }
         // inclusive prefix up to local column c-1 is stored at "c": column c -> [c&3][c>>2]
 #pragma unroll
-        for (int j = 0; j < SK; j++) {
-            const int c = i0 + j + 1;
-            sP[buf][(c & 3) * (ST + 1) + (c >> 2)] = make_uint2(bs + ps[j], bq + pq[j]);
-        }
+        for (int j = 0; j < SK; j++) sP[buf][slot_st[j]] = make_uint2(bs + ps[j], bq + pq[j]);
         if (tid == 0) sP[buf][0] = make_uint2(0u, 0u);            // c = 0: empty prefix
         __syncthreads();
 
@@ -146,19 +156,17 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
         if (is_out) {
             const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
             uint32_t bits = 0;
+            float rn_u = 0.0f;
+            if (nx_uniform) rn_u = __frcp_rn((float)(nxv[0] * ny));
 #pragma unroll
             for (int j = 0; j < SK; j++) {
-                const int x = gx + j;
-                const int i = i0 + j;
-                const int chi = i + p.r + 1, clo = i - p.l + 1;
-                const uint2 hi = sP[buf][(chi & 3) * (ST + 1) + (chi >> 2)];
-                const uint2 lo = sP[buf][(clo & 3) * (ST + 1) + (clo >> 2)];
+                const uint2 hi = sP[buf][slot_hi[j]];
+                const uint2 lo = sP[buf][slot_lo[j]];
                 const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
-                const int nx = min(W, x + p.r + 1) - max(0, x - p.l + 1);
-                const uint32_t n = (uint32_t)(nx * ny);
+                const uint32_t n = (uint32_t)(nxv[j] * ny);
                 uint32_t fg = 0;
-                if (x < W && n > 0) {
-                    const float rn = __frcp_rn((float)n);
+                if (n > 0) {
+                    const float rn = nx_uniform ? rn_u : __frcp_rn((float)n);
                     const uint32_t m = div_fix(S, n, rn);
                     const uint32_t qn = div_fix(Q, n, rn);
                     const int v = (int)qn - (int)(m * m);
