@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
     uint8_t *outSt = rawRec + ISTAGES * rowRec;                               // [3][2][rowOut]
     uint32_t *ringFg = reinterpret_cast<uint32_t *>(outSt + 6 * rowOut);     // [RFG][E]
     uint32_t *ringBg = ringFg + RFG * E;                                     // [RBG][E]
-    uint32_t *ex = ringBg + RBG * E;                                         // [2][5][E]
-    uint32_t *Mtab = ex + 10 * E;                                            // [MAXDEN + 1]
+    uint32_t *ex = ringBg + RBG * E;                                         // [2][4][E]
+    uint32_t *Mtab = ex + 8 * E;                                            // [MAXDEN + 1]
 
     if (tid == 0) {
         s_misc[0] = (int)atomicAdd(p.ticket, 1u);
@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
     }
     __syncthreads();
 
-    uint32_t Cfg_rb[K] = {0, 0}, Cfg_g[K] = {0, 0}, Cbg0[K] = {0, 0}, Cbg1[K] = {0, 0}, Cbg2[K] = {0, 0};
+    // IIR column sums, both layers in 16-bit lanes (r | b<<16, g): a column sum is <= 10*255 and a
+    // 10-column window sum <= 25500, so nothing can carry across a lane
+    uint32_t Cfg_rb[K] = {0, 0}, Cfg_g[K] = {0, 0}, Cbg_rb[K] = {0, 0}, Cbg_g[K] = {0, 0};
+    const uint32_t cvm[K] = {cv[0] ? 0xffffffffu : 0u, cv[1] ? 0xffffffffu : 0u};
     uint32_t prev_fg[K] = {0, 0}, prev_bg[K] = {0, 0}, pf_fg[K] = {0, 0}, pf_bg[K] = {0, 0};
     int pf_row = -1;
     int f_new = RFG - 1, f_old = (RFG - 1 - NFG + RFG) % RFG;     // slots of rows y-1 (write) and y-4 (read)
@@ -385,10 +388,10 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
         if (y >= 1) {
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                if (cv[k]) {
-                    Cfg_rb[k] += lane_rb(prev_fg[k]); Cfg_g[k] += byte_g(prev_fg[k]);
-                    Cbg0[k] += prev_bg[k] & 0xffu; Cbg1[k] += byte_g(prev_bg[k]); Cbg2[k] += (prev_bg[k] >> 16) & 0xffu;
-                }
+                const uint32_t pf = prev_fg[k] & cvm[k], pb = prev_bg[k] & cvm[k];      // columns outside the page hold zeros
+                prev_fg[k] = pf; prev_bg[k] = pb;
+                Cfg_rb[k] += lane_rb(pf); Cfg_g[k] += byte_g(pf);
+                Cbg_rb[k] += lane_rb(pb); Cbg_g[k] += byte_g(pb);
             }
             if (y - NFG - 1 >= 0) {
                 const uint2 t = ld2(ringFg + f_old * E + i0);
@@ -396,18 +399,16 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
             }
             if (y - NBG - 1 >= 0) {
                 const uint2 t = ld2(ringBg + b_old * E + i0);
-                Cbg0[0] -= t.x & 0xffu; Cbg1[0] -= byte_g(t.x); Cbg2[0] -= (t.x >> 16) & 0xffu;
-                Cbg0[1] -= t.y & 0xffu; Cbg1[1] -= byte_g(t.y); Cbg2[1] -= (t.y >> 16) & 0xffu;
+                Cbg_rb[0] -= lane_rb(t.x); Cbg_g[0] -= byte_g(t.x); Cbg_rb[1] -= lane_rb(t.y); Cbg_g[1] -= byte_g(t.y);
             }
-            st2(ringFg + f_new * E + i0, cv[0] ? prev_fg[0] : 0u, cv[1] ? prev_fg[1] : 0u);
-            st2(ringBg + b_new * E + i0, cv[0] ? prev_bg[0] : 0u, cv[1] ? prev_bg[1] : 0u);
+            st2(ringFg + f_new * E + i0, prev_fg[0], prev_fg[1]);
+            st2(ringBg + b_new * E + i0, prev_bg[0], prev_bg[1]);
         }
-        uint32_t *exb = ex + (y & 1) * 5 * E;
+        uint32_t *exb = ex + (y & 1) * 4 * E;
         st2(exb + 0 * E + i0, Cfg_rb[0], Cfg_rb[1]);
         st2(exb + 1 * E + i0, Cfg_g[0], Cfg_g[1]);
-        st2(exb + 2 * E + i0, Cbg0[0], Cbg0[1]);
-        st2(exb + 3 * E + i0, Cbg1[0], Cbg1[1]);
-        st2(exb + 4 * E + i0, Cbg2[0], Cbg2[1]);
+        st2(exb + 2 * E + i0, Cbg_rb[0], Cbg_rb[1]);
+        st2(exb + 3 * E + i0, Cbg_g[0], Cbg_g[1]);
 
         if (tid == 0) {
             tma_wait_read<1>();                              // staging buffer (y % 3) is free again
@@ -449,10 +450,10 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
                 irb[0] = a4.y + a2.x + a2.y; irb[1] = a2.x + a2.y + Cfg_rb[0];
                 ig[0] = b4.y + b2.x + b2.y;  ig[1] = b2.x + b2.y + Cfg_g[0];
             }
-            uint32_t ib[3][K];
+            uint32_t ib[2][K];
             if (need_bg) {   // bg: IIR = sum of C over [c-10, c)
 #pragma unroll
-                for (int w = 0; w < 3; w++) {
+                for (int w = 0; w < 2; w++) {
                     const uint32_t *a = exb + (2 + w) * E + i0;
                     uint32_t acc = 0, first = 0;
 #pragma unroll
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
                         acc += v.x + v.y;
                         if (d == -NBG) first = v.x;
                     }
-                    const uint32_t own = w == 0 ? Cbg0[0] : (w == 1 ? Cbg1[0] : Cbg2[0]);
+                    const uint32_t own = w == 0 ? Cbg_rb[0] : Cbg_g[0];
                     ib[w][0] = acc;
                     ib[w][1] = acc - first + own;
                 }
@@ -472,8 +473,8 @@ __global__ void __launch_bounds__(T) k_opt_iir(const IirParams p)
                 const uint32_t m = hi[k] >> 31;
                 uint32_t nr = lo[k] & 0x1ffffu, ng = (lo[k] >> 17) | ((hi[k] & 3u) << 15), nb = (hi[k] >> 2) & 0x1ffffu;
                 const uint32_t den = min((hi[k] >> 19) & 0xfffu, (uint32_t)MAXDEN);   // clamp: padding columns hold garbage
-                if (m) { nr += ib[0][k]; ng += ib[1][k]; nb += ib[2][k]; }
-                else   { nr += irb[k] & 0xffffu; nb += irb[k] >> 16; ng += ig[k]; }
+                const uint32_t srb = m ? ib[0][k] : irb[k], sg = m ? ib[1][k] : ig[k];
+                nr += srb & 0xffffu; nb += srb >> 16; ng += sg;
                 const uint32_t m31 = Mtab[den];
                 const uint32_t q = div31(nr, m31) | (div31(ng, m31) << 8) | (div31(nb, m31) << 16);
                 ofg_px[k] = m ? rgb[k] : q;
@@ -528,7 +529,7 @@ size_t iir_smem_bytes(int T, int C, int SW)
 {
     const size_t E = (size_t)T * K;
     const size_t rowRGB = ((size_t)SW * C + 15) & ~(size_t)15;
-    return 64 + ISTAGES * (rowRGB + (size_t)SW * 8) + 6 * rowRGB + (size_t)(RFG + RBG + 10) * E * 4 + (MAXDEN + 1) * 4 + 64;
+    return 64 + ISTAGES * (rowRGB + (size_t)SW * 8) + 6 * rowRGB + (size_t)(RFG + RBG + 8) * E * 4 + (MAXDEN + 1) * 4 + 64;
 }
 
 template <int C> const void *fir_kernel(int T)

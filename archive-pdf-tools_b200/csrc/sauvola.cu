@@ -16,8 +16,8 @@
 //     column sums: thread-local prefix -> warp-shuffle inclusive scan -> 8 warp totals in smem;
 //     prefixes are published in a bank-conflict-free SoA layout (column c -> [c&3][c>>2]);
 //   * uint32 wrap-around arithmetic is exact because every window sum is < 2^32 for w <= 255;
-//   * S/n and Q/n use a float reciprocal with an exact +-1 fix-up; the test runs in FP64 with
-//     __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
+//   * S/n and Q/n are exact floors computed on the FP64 pipe (floor((a+0.5)*(1/n))); the test runs in
+//     FP64 with __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
 // Algorithmic HBM bytes: 1 B/px read + 1 B/px written.
 #include "common.cuh"
 
@@ -47,16 +47,6 @@ __device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx
     int valid = W - gx;                  // >= 1
     if (valid < 4) w &= (1u << (8 * valid)) - 1u;
     return w;
-}
-
-// floor(a / n) for a < 2^32, n >= 1, a / n <= 65025, rn ~= 1/n (relative error <= 2^-22)
-__device__ __forceinline__ uint32_t div_fix(uint32_t a, uint32_t n, float rn)
-{
-    uint32_t q = (uint32_t)(__uint2float_rz(a) * rn);
-    uint32_t prod = q * n;
-    if (prod > a) { q--; prod -= n; }
-    if (a - prod >= n) q++;
-    return q;
 }
 
 __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
@@ -156,25 +146,28 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
         if (is_out) {
             const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
             uint32_t bits = 0;
-            float rn_u = 0.0f;
-            if (nx_uniform) rn_u = __frcp_rn((float)(nxv[0] * ny));
+            // S/n and Q/n on the (otherwise idle) FP64 pipe: floor((a + 0.5) * (1/n)) == a / n exactly,
+            // because (a + 0.5)/n is at least 1/(2n) away from every integer while the double product is
+            // accurate to 2^-52 relative (a < 2^32, n <= 65025).  The quotients come out as the doubles
+            // the test needs, so no int->double conversions of m and v remain.
+            double rn_u = 0.0;
+            if (nx_uniform) rn_u = 1.0 / (double)(nxv[0] * ny);
 #pragma unroll
             for (int j = 0; j < SK; j++) {
                 const uint2 hi = sP[buf][slot_hi[j]];
                 const uint2 lo = sP[buf][slot_lo[j]];
                 const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
-                const uint32_t n = (uint32_t)(nxv[j] * ny);
+                const int n = nxv[j] * ny;
                 uint32_t fg = 0;
                 if (n > 0) {
-                    const float rn = nx_uniform ? rn_u : __frcp_rn((float)n);
-                    const uint32_t m = div_fix(S, n, rn);
-                    const uint32_t qn = div_fix(Q, n, rn);
-                    const int v = (int)qn - (int)(m * m);
-                    const double md = (double)m;
-                    const double mm = (double)(m * m);
+                    const double rn = nx_uniform ? rn_u : 1.0 / (double)n;
+                    const double md = floor(__dmul_rn(__dadd_rn((double)S, 0.5), rn));      // (double)(S / n)
+                    const double qd = floor(__dmul_rn(__dadd_rn((double)Q, 0.5), rn));      // (double)(Q / n)
+                    const double mm = __dmul_rn(md, md);                                     // exact (integers < 2^53)
+                    const double v = __dadd_rn(qd, -mm);
                     const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
                     const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
-                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), (double)v);
+                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
                     const double lhs = __dmul_rn(t, t);
                     if (p.kneg) fg = (t <= 0.0) && (lhs >= rhs);
                     else        fg = (t <= 0.0) || (lhs <= rhs);

@@ -316,3 +316,63 @@ class DecomposeBatch:
         if self.bg_plan:
             stage('bg_thumbnail', lambda: eng.resample(self.bg_plan, bgf, self.bg))
         return self
+
+
+class StreamedDecomposer:
+    """Host-to-host decomposition of a large batch in chunks: H2D of chunk i+1, the kernels of chunk i
+    and D2H of chunk i-1 run concurrently on three streams over double-buffered device batches, so
+    the PCIe link (full duplex) is the only exposed cost.  Host tensors should be pinned."""
+
+    def __init__(self, eng, n_pages, h, w, c, chunk=16, bg_downsample=None, fg_downsample=None, mask_only=False):
+        self.eng, self.n, self.h, self.w, self.c = eng, n_pages, h, w, c
+        self.chunk = max(1, min(chunk, n_pages))
+        self.batches = [eng.make_batch(self.chunk, h, w, c, bg_downsample, fg_downsample, mask_only) for _ in range(2)]
+        self.mask_only = mask_only
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=eng.device) for _ in range(3))
+        b = self.batches[0]
+        self.out_shapes = dict(mask=(h, w), fg=None if mask_only else (b.fg.h, b.fg.w * c), bg=None if mask_only else (b.bg.h, b.bg.w * c))
+        self.errors = set(b.errors)
+
+    def alloc_outputs(self):
+        """Pinned host result buffers: mask [N,H,W] u8 (0/1), fg [N,fh,fw*C], bg [N,bh,bw*C]."""
+        o = {'mask': torch.empty((self.n,) + self.out_shapes['mask'], dtype=torch.uint8).pin_memory()}
+        if not self.mask_only:
+            o['fg'] = torch.empty((self.n,) + self.out_shapes['fg'], dtype=torch.uint8).pin_memory()
+            o['bg'] = torch.empty((self.n,) + self.out_shapes['bg'], dtype=torch.uint8).pin_memory()
+        return o
+
+    def run(self, host_pages, out, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST):
+        """host_pages: CPU uint8 tensor [N,H,W(,C)]; out: dict from alloc_outputs().  Returns after
+        everything has landed in `out` (one final stream synchronisation)."""
+        n, ck = self.n, self.chunk
+        hp = host_pages.reshape(n, self.h, self.w * self.c)
+        cur = torch.cuda.current_stream()
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        in_done, cmp_done, out_done = {}, {}, {}
+        n_chunks = (n + ck - 1) // ck
+        for i in range(n_chunks):
+            lo, hi = i * ck, min(n, (i + 1) * ck)
+            m = hi - lo
+            b = self.batches[i % 2]
+            with torch.cuda.stream(self.s_in):
+                if i >= 2:
+                    self.s_in.wait_event(cmp_done[i - 2])          # img buffer of this slot is free again
+                b.img.view()[:m].copy_(hp[lo:hi].to(self.eng.device, non_blocking=True))
+                in_done[i] = self.s_in.record_event()
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(in_done[i])
+                if i >= 2:
+                    self.s_cmp.wait_event(out_done[i - 2])         # output planes of this slot were drained
+                b.run(window, k, R, denoise_mask)                  # b200mrc_decompose on the chunk (a short tail chunk recomputes stale pages: harmless)
+                cmp_done[i] = self.s_cmp.record_event()
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(cmp_done[i])
+                out['mask'][lo:hi].copy_(b.mask.view()[:m], non_blocking=True)
+                if not self.mask_only:
+                    out['fg'][lo:hi].copy_(b.fg.view()[:m], non_blocking=True)
+                    out['bg'][lo:hi].copy_(b.bg.view()[:m], non_blocking=True)
+                out_done[i] = self.s_out.record_event()
+        cur.wait_stream(self.s_out)
+        self.s_out.synchronize()
+        return out
