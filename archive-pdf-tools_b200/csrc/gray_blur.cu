@@ -224,6 +224,9 @@ __device__ __forceinline__ uint32_t load_gray4(const GrayBlurParams &p, const ui
     return r;
 }
 
+// (double)x for 0 <= x < 2^31 without the conversion unit: 2^52 + x is exact, subtract 2^52 on the FP64 pipe
+__device__ __forceinline__ double u2d(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+
 template <int R, int C>
 __device__ __forceinline__ void blur_march(const GrayBlurParams &p, const uint8_t *in, uint8_t *out,
                                            int x, int by0, int by1, const double *sw)
@@ -242,10 +245,10 @@ __device__ __forceinline__ void blur_march(const GrayBlurParams &p, const uint8_
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            double acc = __dmul_rn((double)(int)((win[R] >> (8 * k)) & 0xff), w[0]);
+            double acc = __dmul_rn(u2d((win[R] >> (8 * k)) & 0xff), w[0]);
 #pragma unroll
             for (int j = R; j >= 1; j--)
-                acc = __dadd_rn(acc, __dmul_rn((double)(int)(((win[R - j] >> (8 * k)) & 0xff) + ((win[R + j] >> (8 * k)) & 0xff)), w[j]));
+                acc = __dadd_rn(acc, __dmul_rn(u2d(((win[R - j] >> (8 * k)) & 0xff) + ((win[R + j] >> (8 * k)) & 0xff)), w[j]));
             v[k] = __double2float_rn(acc);
         }
         uint32_t o = 0;
@@ -257,9 +260,9 @@ __device__ __forceinline__ void blur_march(const GrayBlurParams &p, const uint8_
 #pragma unroll
             for (int k = 0; k < 4; k++) ext[R + k] = (double)v[k];
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-                ext[j] = (double)__shfl_up_sync(0xffffffffu, v[4 - R + j], 1);
-                ext[R + 4 + j] = (double)__shfl_down_sync(0xffffffffu, v[j], 1);
+            for (int j = 0; j < R; j++) {      // neighbours' values arrive already widened (shuffle, not convert)
+                ext[j] = __shfl_up_sync(0xffffffffu, ext[R + 4 - R + j], 1);
+                ext[R + 4 + j] = __shfl_down_sync(0xffffffffu, ext[R + j], 1);
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {

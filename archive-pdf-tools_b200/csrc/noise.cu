@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(256) k_noise_dd(const NoiseParams p)
         dd = __fadd_rn(dd, __fmul_rn(f[j2], d0));
     }
     const uint32_t key = dd == 0.0f ? 0u : (__float_as_uint(dd) & 0x7fffffffu);
-    p.keys[(int64_t)page * p.oh * p.ow + (int64_t)yo * p.ow + xo] = key;
+    const int64_t stride = ((int64_t)p.oh * p.ow + 3) & ~3ll;
+    p.keys[(int64_t)page * stride + (int64_t)yo * p.ow + xo] = key;
+    if (yo == p.oh - 1 && xo == p.ow - 1)
+        for (int64_t q = (int64_t)p.oh * p.ow; q < stride; q++) p.keys[(int64_t)page * stride + q] = 0u;
 }
 
 constexpr int SEL_T = 1024;
@@ -112,15 +115,19 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
     __shared__ uint32_t s_scan[32];
     __shared__ uint32_t s_res[2];
     const int page = blockIdx.x, tid = threadIdx.x;
-    const int64_t total = (int64_t)p.oh * p.ow;
+    const int64_t total = ((int64_t)p.oh * p.ow + 3) & ~3ll;          // per-page key stride: padded with zeros to 4
     const uint32_t *keys = p.keys + (int64_t)page * total;
 
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
     // pass 1: top 12 bits (non-zero keys only)
-    for (int64_t i = tid; i < total; i += SEL_T) {
-        const uint32_t k = keys[i];
-        if (k) atomicAdd(&hist[0][k >> 20], 1u);
+    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
+        const int64_t i2 = i + SEL_T * 4;
+        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (kk[q]) atomicAdd(&hist[0][kk[q] >> 20], 1u);
     }
     __syncthreads();
     uint32_t cnt;
@@ -151,12 +158,19 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
     // pass 2: middle 10 bits under each target prefix
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int64_t i = tid; i < total; i += SEL_T) {
-        const uint32_t k = keys[i];
-        if (!k) continue;
-        const uint32_t top = k >> 20, mid = (k >> 10) & 0x3ffu;
-        if (top == pre[0]) atomicAdd(&hist[0][mid], 1u);
-        if (top == pre[1]) atomicAdd(&hist[1][mid], 1u);
+    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
+        const int64_t i2 = i + SEL_T * 4;
+        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t k = kk[q];
+            if (!k) continue;
+            const uint32_t top = k >> 20, mid = (k >> 10) & 0x3ffu;
+            if (top == pre[0]) atomicAdd(&hist[0][mid], 1u);
+            if (top == pre[1]) atomicAdd(&hist[1][mid], 1u);
+        }
     }
     __syncthreads();
     for (int t = 0; t < 2; t++) {
@@ -167,12 +181,19 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
     // pass 3: low 10 bits
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int64_t i = tid; i < total; i += SEL_T) {
-        const uint32_t k = keys[i];
-        if (!k) continue;
-        const uint32_t hi = k >> 10, lo = k & 0x3ffu;
-        if (hi == pre[0]) atomicAdd(&hist[0][lo], 1u);
-        if (hi == pre[1]) atomicAdd(&hist[1][lo], 1u);
+    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
+        const int64_t i2 = i + SEL_T * 4;
+        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t k = kk[q];
+            if (!k) continue;
+            const uint32_t hi = k >> 10, lo = k & 0x3ffu;
+            if (hi == pre[0]) atomicAdd(&hist[0][lo], 1u);
+            if (hi == pre[1]) atomicAdd(&hist[1][lo], 1u);
+        }
     }
     __syncthreads();
     for (int t = 0; t < 2; t++) {
@@ -204,7 +225,7 @@ size_t noise_workspace_bytes(int W, int H, int N)
     int hs, he, ws, we;
     noise_crop(W, H, hs, he, ws, we);
     const size_t oh = (size_t)(he - hs + 3) / 2, ow = (size_t)(we - ws + 3) / 2;
-    return align_up(sizeof(uint32_t) * oh * ow * (size_t)N, 256);
+    return align_up(sizeof(uint32_t) * ((oh * ow + 3) & ~(size_t)3) * (size_t)N, 256);
 }
 
 int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C, int W, int H, int N,

@@ -105,16 +105,30 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
             for (int j = 0; j < SK; j++) sP[b][j * (ST + 1)] = make_uint2(0u, 0u);   // never used: c=0 slot set below
     }
 
+    // loads run two rows ahead of their use (L2/HBM latency >> one row step): stage A feeds the
+    // next iteration, stage B the one after
+    auto load_upd = [&](int yu, uint32_t &we, uint32_t &wl, uint32_t &wc) {
+        // words needed to move the window from row yu-1 to row yu, and row yu's own pixels
+        we = 0; wl = 0; wc = 0;
+        if (yu < by1) {
+            const int ye = yu + p.u, yl = yu - p.o;
+            if (ye < H) we = load_word_clamped(in + (int64_t)ye * p.in_pitch, gx, W);
+            if (yl >= 0) wl = load_word_clamped(in + (int64_t)yl * p.in_pitch, gx, W);
+            wc = load_word_clamped(in + (int64_t)yu * p.in_pitch, gx, W);
+        }
+    };
+    uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W);
+    uint32_t weA, wlA, wcA, weB, wlB, wcB;
+    load_upd(by0 + 1, weA, wlA, wcA);
+    load_upd(by0 + 2, weB, wlB, wcB);
+    int ny_cached = -1;
+    double rn_u = 0.0;
+
     for (int y = by0; y < by1; y++) {
         const int buf = (y - by0) & 1;
-        // issue the loads this iteration needs early
-        const uint32_t wcur = load_word_clamped(in + (int64_t)y * p.in_pitch, gx, W);
-        const int ye = y + 1 + p.u, yl = y + 1 - p.o;
-        uint32_t wenter = 0, wleave = 0;
-        if (y + 1 < by1) {
-            if (ye < H) wenter = load_word_clamped(in + (int64_t)ye * p.in_pitch, gx, W);
-            if (yl >= 0) wleave = load_word_clamped(in + (int64_t)yl * p.in_pitch, gx, W);
-        }
+        const uint32_t wenter = weA, wleave = wlA, wnext = wcA;
+        weA = weB; wlA = wlB; wcA = wcB;
+        load_upd(y + 3, weB, wlB, wcB);
 
         // ---- prefix of the column sums across the CTA
         uint32_t ps[SK], pq[SK];
@@ -150,8 +164,7 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
             // because (a + 0.5)/n is at least 1/(2n) away from every integer while the double product is
             // accurate to 2^-52 relative (a < 2^32, n <= 65025).  The quotients come out as the doubles
             // the test needs, so no int->double conversions of m and v remain.
-            double rn_u = 0.0;
-            if (nx_uniform) rn_u = 1.0 / (double)(nxv[0] * ny);
+            if (nx_uniform && ny != ny_cached) { rn_u = 1.0 / (double)(nxv[0] * ny); ny_cached = ny; }
 #pragma unroll
             for (int j = 0; j < SK; j++) {
                 const uint2 hi = sP[buf][slot_hi[j]];
@@ -196,6 +209,7 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
             cs[j] += a - b;
             cq[j] += a * a - b * b;
         }
+        wcur = wnext;
     }
 }
 
