@@ -39,6 +39,8 @@ PROTOTYPES = {
     'b200mrc_version': (C.c_int, []),
     'b200mrc_error_string': (C.c_char_p, [C.c_int]),
     'b200mrc_launch_count': (C.c_uint64, []),
+    'b200mrc_profile_enable': (C.c_int, [C.c_int]),
+    'b200mrc_profile_report': (C.c_int, [C.c_char_p, C.c_size_t]),
     'b200mrc_rgb2gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]),
     'b200mrc_sauvola': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, vp]),
@@ -89,3 +91,18 @@ def check(status, what=''):
     if status != 0:
         msg = lib().b200mrc_error_string(status)
         raise B200MrcError('%s failed (%d): %s' % (what or 'b200mrc call', status, msg.decode() if msg else '?'))
+
+
+def profile_enable(on=True):
+    check(lib().b200mrc_profile_enable(1 if on else 0), 'b200mrc_profile_enable')
+
+
+def profile_report():
+    """{kernel: (launches, total_ms)} for the launches recorded since profile_enable(True)."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().b200mrc_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(',', 2)
+        out[name] = (int(n), float(ms))
+    return out

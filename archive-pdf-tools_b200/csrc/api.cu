@@ -10,12 +10,35 @@
 #include "common.cuh"
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <string>
+#include <vector>
 
 struct b200mrc_resample_plan;
 
 namespace b200mrc {
 
 std::atomic<uint64_t> g_launch_count{0};
+
+namespace {
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+bool g_prof_on = false;
+}  // namespace
+
+void prof_begin(const char *kernel, cudaStream_t st)
+{
+    if (!g_prof_on) return;
+    ProfRec r{kernel, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st)
+{
+    if (!g_prof_on || g_prof.empty()) return;
+    cudaEventRecord(g_prof.back().b, st);
+}
 
 const DevInfo &dev_info()
 {
@@ -103,6 +126,36 @@ int check_args(const b200mrc_decompose_args *a)
 using namespace b200mrc;
 
 extern "C" int b200mrc_version(void) { return B200MRC_VERSION; }
+
+extern "C" int b200mrc_profile_enable(int on)
+{
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return B200MRC_OK;
+}
+
+extern "C" int b200mrc_profile_report(char *buf, size_t cap)
+{
+    // "kernel,launches,total_ms" lines; synchronises with every recorded event
+    std::map<std::string, std::pair<int, double>> acc;
+    std::vector<std::string> order;
+    for (auto &r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        if (!acc.count(r.name)) order.push_back(r.name);
+        acc[r.name].first += 1; acc[r.name].second += ms;
+    }
+    std::string out;
+    for (auto &n : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s,%d,%.6f\n", n.c_str(), acc[n].first, acc[n].second);
+        out += line;
+    }
+    if (buf && cap) { strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
+    return (int)out.size();
+}
 
 extern "C" uint64_t b200mrc_launch_count(void) { return g_launch_count.load(); }
 

@@ -28,6 +28,16 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
         if (_e != cudaSuccess) return (int)_e;                   \
     } while (0)
 
+// Optional per-kernel CUDA-event timing (b200mrc_profile_enable / b200mrc_profile_report): an event
+// pair is recorded on the launching stream around every kernel while profiling is on.
+void prof_begin(const char *kernel, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    ProfScope(const char *kernel, cudaStream_t s) : st(s) { prof_begin(kernel, s); }
+    ~ProfScope() { prof_end(st); }
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -302,7 +302,7 @@ int launch_denoise(uint8_t *mask, int64_t pitch, int64_t stride, int W, int H, i
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     void *args[] = {(void *)&p};
-    B200MRC_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_mask_denoise, dim3(grid), dim3(DT), args, 0, st));
+    { ProfScope _ps("k_mask_denoise", st); B200MRC_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_mask_denoise, dim3(grid), dim3(DT), args, 0, st)); }
     count_launch();
     return B200MRC_OK;
 }

@@ -325,8 +325,9 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
                          !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
     if (fast_ok) {
         dim3 grid(cdiv(W, 120), cdiv(cdiv(H, FB_BAND), 8), N);
-        if (C == 1) k_gray_blur_fast<1><<<grid, 256, 0, st>>>(p);
-        else k_gray_blur_fast<3><<<grid, 256, 0, st>>>(p);
+        { ProfScope _ps("k_gray_blur_fast", st);
+          if (C == 1) k_gray_blur_fast<1><<<grid, 256, 0, st>>>(p);
+          else k_gray_blur_fast<3><<<grid, 256, 0, st>>>(p); }
         B200MRC_LAUNCH_CHECK();
         p.rlo = 5;
     }
@@ -336,7 +337,7 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
         B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur<RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(cdiv(W, TW), cdiv(H, TH), N);
-        k_gray_blur<RHI, TH, TW><<<grid, 256, smem, st>>>(p);
+        { ProfScope _ps("k_gray_blur", st); k_gray_blur<RHI, TH, TW><<<grid, 256, smem, st>>>(p); }
         B200MRC_LAUNCH_CHECK();
     } else if (sigma) {
         // radius 5..16: persistent CTAs walk the pages and share the tiles of those that need it
@@ -346,7 +347,7 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
         const int tiles = cdiv(W, TW) * cdiv(H, TH);
         int grid = dev_info().sm_count * 4;
         if (grid > tiles) grid = tiles;
-        k_gray_blur_large<5, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N);
+        { ProfScope _ps("k_gray_blur_large<5..16>", st); k_gray_blur_large<5, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
         B200MRC_LAUNCH_CHECK();
     }
     if (sigma) {
@@ -356,7 +357,7 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
         const int tiles = cdiv(W, TW) * cdiv(H, TH);
         int grid = dev_info().sm_count * 2;
         if (grid > tiles) grid = tiles;
-        k_gray_blur_large<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N);
+        { ProfScope _ps("k_gray_blur_large<17..128>", st); k_gray_blur_large<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
         B200MRC_LAUNCH_CHECK();
     }
     return B200MRC_OK;

@@ -239,9 +239,9 @@ int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride
     p.keys = (uint32_t *)workspace;
     p.sigma_out = sigma_out;
     dim3 grid(cdiv(p.ow, 32), cdiv(p.oh, 8), N);
-    k_noise_dd<<<grid, 256, 0, st>>>(p);
+    { ProfScope _ps("k_noise_dd", st); k_noise_dd<<<grid, 256, 0, st>>>(p); }
     B200MRC_LAUNCH_CHECK();
-    k_noise_select<<<N, SEL_T, 0, st>>>(p);
+    { ProfScope _ps("k_noise_select", st); k_noise_select<<<N, SEL_T, 0, st>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

@@ -349,7 +349,7 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     B200MRC_CUDA_TRY(cudaMemsetAsync(p.prog, 0, sizeof(int) * (size_t)N * plan.S, st));
     B200MRC_CUDA_TRY(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned) * 4, st));
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_optimise_fg_bg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    k_optimise_fg_bg<<<(unsigned)(plan.S * N), plan.T, plan.smem, st>>>(p);
+    { ProfScope _ps("k_optimise_fg_bg", st); k_optimise_fg_bg<<<(unsigned)(plan.S * N), plan.T, plan.smem, st>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

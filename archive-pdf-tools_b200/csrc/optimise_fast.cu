@@ -558,7 +558,7 @@ int launch_optimise_fast(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     const void *kern = pick_kernel(plan.K, C);
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     void *args[] = {(void *)&p};
-    B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3((unsigned)(plan.S * N)), dim3(plan.T), args, plan.smem, st));
+    { ProfScope _ps("k_optimise_3_10", st); B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3((unsigned)(plan.S * N)), dim3(plan.T), args, plan.smem, st)); }
     count_launch();
     return B200MRC_OK;
 }

@@ -320,7 +320,7 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         r.C = pl->C; r.bx = pl->rx0; r.by = pl->ry0; r.bw = pl->rx1 - pl->rx0; r.bh = pl->ry1 - pl->ry0;
         r.fx = pl->fx; r.fy = pl->fy; r.out_w = pl->SW; r.out_h = pl->SH;
         dim3 grid(cdiv(pl->SW * pl->C, 256), pl->SH, n_pages);
-        k_reduce_box<<<grid, 256, 0, st>>>(r);
+        { ProfScope _ps("k_reduce_box", st); k_reduce_box<<<grid, 256, 0, st>>>(r); }
         B200MRC_LAUNCH_CHECK();
         src = red; src_pitch = r.out_pitch; src_stride = r.out_stride;
     }
@@ -338,8 +338,9 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         h.C = pl->C; h.in_w = pl->SW; h.in_h = pl->SH; h.out_w = pl->OW; h.out_h = pl->SH; h.ksize = pl->ksize_h;
         h.bounds = pl->d_bounds_h; h.kk = pl->d_kk_h;
         dim3 grid(cdiv(pl->OW, 128), cdiv(pl->SH, H_RPT), n_pages);
-        if (pl->C == 1) k_resample_h<1><<<grid, 128, 0, st>>>(h);
-        else k_resample_h<3><<<grid, 128, 0, st>>>(h);
+        { ProfScope _ps("k_resample_h", st);
+          if (pl->C == 1) k_resample_h<1><<<grid, 128, 0, st>>>(h);
+          else k_resample_h<3><<<grid, 128, 0, st>>>(h); }
         B200MRC_LAUNCH_CHECK();
         src = h.out; src_pitch = h.out_pitch; src_stride = h.out_stride;
     }
@@ -351,7 +352,7 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         v.bounds = pl->d_bounds_v; v.kk = pl->d_kk_v;
         if ((src_pitch & 3) || (src_stride & 3) || ((uintptr_t)src & 3)) return B200MRC_ERR_ALIGNMENT;
         dim3 grid(cdiv(cdiv(pl->OW * pl->C, 4), 256), pl->OH, n_pages);
-        k_resample_v<<<grid, 256, 0, st>>>(v);
+        { ProfScope _ps("k_resample_v", st); k_resample_v<<<grid, 256, 0, st>>>(v); }
         B200MRC_LAUNCH_CHECK();
     }
     return B200MRC_OK;

@@ -252,7 +252,7 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     p.flags = flags;
 
     dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_pages);
-    k_sauvola_mask<<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+    { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream); k_sauvola_mask<<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

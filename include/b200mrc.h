@@ -63,6 +63,11 @@ B200MRC_API int         b200mrc_version(void);
 B200MRC_API const char *b200mrc_error_string(int status);
 /* number of CUDA kernels this library has launched in the calling process (bench bookkeeping) */
 B200MRC_API uint64_t    b200mrc_launch_count(void);
+/* Per-kernel device timing: while enabled, every kernel launch of this library is bracketed by a CUDA
+ * event pair on its own stream.  b200mrc_profile_report synchronises and writes "kernel,launches,total_ms"
+ * lines into buf (returns the full length); enable(0/1) also clears the records. */
+B200MRC_API int         b200mrc_profile_enable(int on);
+B200MRC_API int         b200mrc_profile_report(char *buf, size_t cap);
 
 /* A1  PIL convert('L') (mrc.py:361): L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16. */
 B200MRC_API int b200mrc_rgb2gray(const uint8_t *rgb, int64_t rgb_pitch, int64_t rgb_page_stride,
