@@ -13,6 +13,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_ALIGNMENT = 0, -1, -2, -3, 
 SAUVOLA_OR_INTO, SAUVOLA_RAW_INVERTED = 1, 2
 DECOMPOSE_DENOISE_FAST, DECOMPOSE_MASK_ONLY, DECOMPOSE_NO_NOISE_EST = 1, 2, 4
 MAX_WINDOW, MAX_OPT_N = 255, 16
+COPY_H2D, COPY_D2H, COPY_D2D = 1, 2, 3
 
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
@@ -41,6 +42,7 @@ PROTOTYPES = {
     'b200mrc_launch_count': (C.c_uint64, []),
     'b200mrc_profile_enable': (C.c_int, [C.c_int]),
     'b200mrc_profile_report': (C.c_int, [C.c_char_p, C.c_size_t]),
+    'b200mrc_copy2d': (C.c_int, [vp, i64, vp, i64, i64, i64, C.c_int, vp]),
     'b200mrc_rgb2gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]),
     'b200mrc_sauvola': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, vp]),

@@ -173,6 +173,19 @@ extern "C" const char *b200mrc_error_string(int status)
     return "b200mrc: unknown error";
 }
 
+extern "C" int b200mrc_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
+                              int64_t row_bytes, int64_t rows, int kind, void *stream)
+{
+    if (!dst || !src || row_bytes < 0 || rows < 0 || dst_pitch < row_bytes || src_pitch < row_bytes) return B200MRC_ERR_INVALID;
+    if (kind < B200MRC_COPY_H2D || kind > B200MRC_COPY_D2D) return B200MRC_ERR_INVALID;
+    if (row_bytes == 0 || rows == 0) return B200MRC_OK;
+    const cudaMemcpyKind k = kind == B200MRC_COPY_H2D ? cudaMemcpyHostToDevice
+                           : (kind == B200MRC_COPY_D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    B200MRC_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)rows, k,
+                                       (cudaStream_t)stream));
+    return B200MRC_OK;
+}
+
 extern "C" size_t b200mrc_decompose_workspace_bytes(const b200mrc_decompose_args *a)
 {
     if (check_args(a) != B200MRC_OK) return 0;

@@ -32,6 +32,8 @@
 #include <cstdlib>
 
 namespace b200mrc {
+size_t iirg_mailbox_bytes(int W, int H, int N);       // optimise_ghost.cu
+size_t optimise_split_rec_bytes(int W, int H, int N);  // optimise_split.cu
 namespace {
 
 constexpr int OH = 16;                 // halo columns each side (>= B200MRC_MAX_OPT_N)
@@ -286,10 +288,10 @@ OptLayout opt_layout(int W, int H, int N)
     const size_t Smax = (size_t)cdiv(W, 32);
     Carver c;
     OptLayout L;
-    L.off_mailbox = c.take<uint32_t>((size_t)N * Smax * H * 2 * OH);
+    L.off_mailbox = c.take<uint32_t>(std::max((size_t)N * Smax * H * 2 * OH, iirg_mailbox_bytes(W, H, N) / sizeof(uint32_t)));
     L.off_prog = c.take<int>((size_t)N * Smax);
     L.off_ticket = c.take<unsigned>(4);
-    L.off_rec = c.take<uint8_t>(align_up((size_t)W * 8, 16) * (size_t)H * (size_t)N);   // FIR record plane (optimise_split.cu)
+    L.off_rec = c.take<uint8_t>(optimise_split_rec_bytes(W, H, N));   // FIR record plane (optimise_split.cu)
     L.total = c.used();
     return L;
 }

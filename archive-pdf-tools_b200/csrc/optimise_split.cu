@@ -27,6 +27,8 @@
 // arithmetic.
 #include "common.cuh"
 #include "tma.cuh"
+#include <cstring>
+#include <cstdlib>
 
 namespace b200mrc {
 namespace {
@@ -148,6 +150,7 @@ struct FirParams {
     const uint8_t *img;  int64_t ipitch, istride;
     uint8_t *rec; int64_t rpitch, rstride;         // 8 B / pixel
     int W, H, S, SW, n_bands, band_h;
+    int fmt;                                       // 0: legacy records; 1: 16-bit-lane fg records (optimise_warp.cu)
 };
 
 template <int C, int K, int T>
@@ -287,9 +290,9 @@ __global__ void __launch_bounds__(T) k_opt_fir(const FirParams p)
             for (int k = 0; k < K; k++) any_m |= cur[k] & 0x01000000u;
             const bool need_bg = __any_sync(__activemask(), any_m != 0);
             uint32_t num_r[K], num_g[K], num_b[K], den[K];
+            uint32_t s[2][K];
             {   // fg: sum of F over [c-3, c+3), slid across the K columns (16-bit lanes)
                 constexpr int NL = (NFG + K - 1) / K * K;
-                uint32_t s[2][K];
 #pragma unroll
                 for (int w = 0; w < 2; w++) {
                     uint32_t a[NL + 2 * K];
@@ -347,6 +350,11 @@ __global__ void __launch_bounds__(T) k_opt_fir(const FirParams p)
             for (int k = 0; k < K; k++) {
                 o[2 * k] = num_r[k] | (num_g[k] << 17);
                 o[2 * k + 1] = (num_g[k] >> 15) | (num_b[k] << 2) | (den[k] << 19) | ((cur[k] & 0x01000000u) << 7);
+                if (p.fmt == 1 && !(cur[k] & 0x01000000u)) {
+                    // fg-type pixel, lanes form: 2*Fr | 2*Fb << 16 ; 2*Fg | 4*den << 16  (bit 31 stays clear: den <= 45)
+                    o[2 * k] = s[0][k] << 1;
+                    o[2 * k + 1] = ((s[1][k] & 0xffffu) << 1) | (den[k] << 18);
+                }
             }
             uint32_t *dst = reinterpret_cast<uint32_t *>(outSt + ob * rowOut + (i0 - FH) * 8);
             if (K == 1) *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
@@ -765,9 +773,24 @@ int plan_split(int W, int H, int N, int C, SplitPlan &out)
 
 }  // namespace
 
+int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                        const uint8_t *rec, int64_t rpitch, int64_t rstride,
+                        uint8_t *ofg, int64_t fpitch, int64_t fstride,
+                        uint8_t *obg, int64_t bpitch, int64_t bstride,
+                        int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, cudaStream_t st);
+
+int launch_opt_iir_ghost(const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                         const uint8_t *rec, int64_t rpitch, int64_t rstride,
+                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
+                         uint8_t *obg, int64_t bpitch, int64_t bstride,
+                         int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int K, int wpc, cudaStream_t st);
+void iirg_forget(const void *mailbox);
+int64_t iirg_rec_pitch(int W);
+
+// record plane: 8 B / pixel, rows padded to whole 4-pixel groups (optimise_ghost.cu reads whole groups)
 size_t optimise_split_rec_bytes(int W, int H, int N)
 {
-    return align_up((size_t)W * 8, 16) * (size_t)H * (size_t)N;
+    return (size_t)iirg_rec_pitch(W) * (size_t)H * (size_t)N;
 }
 
 // Returns B200MRC_ERR_UNSUPPORTED when this path does not apply (the caller falls back).
@@ -787,9 +810,15 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     SplitPlan pl;
     int rc = plan_split(W, H, N, C, pl);
     if (rc != B200MRC_OK) return rc;
-    const int64_t rpitch = (int64_t)align_up((size_t)W * 8, 16), rstride = rpitch * H;
+    const int64_t rpitch = iirg_rec_pitch(W), rstride = rpitch * H;
+    // IIR sweep: "warp" (default: optimise_warp.cu) | "ghost" (optimise_ghost.cu, experimental) | "cta" (k_opt_iir below)
+    const char *iir_sel = getenv("B200MRC_IIR");
+    const bool ghost_iir = iir_sel && !strcmp(iir_sel, "ghost");
+    const bool warp_iir = ghost_iir || !iir_sel || strcmp(iir_sel, "cta") != 0;   // both read fmt-1 records
+    if (!ghost_iir) iirg_forget(mailbox);
     {
         FirParams p;
+        p.fmt = warp_iir ? 1 : 0;
         p.mask = mask; p.mpitch = mpitch; p.mstride = mstride; p.img = img; p.ipitch = ipitch; p.istride = istride;
         p.rec = rec; p.rpitch = rpitch; p.rstride = rstride;
         p.W = W; p.H = H; p.S = pl.fS; p.SW = pl.fSW; p.n_bands = pl.bands; p.band_h = pl.band_h;
@@ -799,6 +828,12 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
         { ProfScope _ps("k_opt_fir", st); B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3((unsigned)(pl.fS * pl.bands), (unsigned)N), dim3(pl.fT), args, pl.fsmem, st)); }
         count_launch();
     }
+    if (ghost_iir)
+        return launch_opt_iir_ghost(img, ipitch, istride, C, rec, rpitch, rstride, ofg, fpitch, fstride, obg, bpitch, bstride,
+                                    W, H, N, mailbox, ticket, env_int("B200MRC_IIRG_K", 4), env_int("B200MRC_IIRG_WPC", 2), st);
+    if (warp_iir)
+        return launch_opt_iir_warp(img, ipitch, istride, C, rec, rpitch, rstride, ofg, fpitch, fstride, obg, bpitch, bstride,
+                                   W, H, N, mailbox, ticket, env_int("B200MRC_IIRW_WPC", 2), st);
     {
         IirParams p;
         p.img = img; p.ipitch = ipitch; p.istride = istride; p.rec = rec; p.rpitch = rpitch; p.rstride = rstride;

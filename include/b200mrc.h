@@ -69,6 +69,17 @@ B200MRC_API uint64_t    b200mrc_launch_count(void);
 B200MRC_API int         b200mrc_profile_enable(int on);
 B200MRC_API int         b200mrc_profile_report(char *buf, size_t cap);
 
+/* Page transfer between HOST memory (pinned for true asynchrony) and pitched device planes: what
+ * np.array(image) / returning a numpy array is at the reference's boundary (mrc.py:372, 399, 436,
+ * 470).  `rows` rows of `row_bytes` bytes each; a whole batch is one call when page_stride ==
+ * height * pitch (rows = n_pages * height).  kind: 1 = host to device, 2 = device to host,
+ * 3 = device to device.  One DMA (cudaMemcpy2DAsync) on `stream`: no staging copy, no kernel. */
+#define B200MRC_COPY_H2D 1
+#define B200MRC_COPY_D2H 2
+#define B200MRC_COPY_D2D 3
+B200MRC_API int b200mrc_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
+                   int64_t row_bytes, int64_t rows, int kind, void *stream);
+
 /* A1  PIL convert('L') (mrc.py:361): L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16. */
 B200MRC_API int b200mrc_rgb2gray(const uint8_t *rgb, int64_t rgb_pitch, int64_t rgb_page_stride,
                      uint8_t *gray, int64_t gray_pitch, int64_t gray_page_stride,
