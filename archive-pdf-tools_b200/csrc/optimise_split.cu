@@ -786,6 +786,10 @@ int launch_opt_iir_ghost(const uint8_t *img, int64_t ipitch, int64_t istride, in
                          int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int K, int wpc, cudaStream_t st);
 void iirg_forget(const void *mailbox);
 int64_t iirg_rec_pitch(int W);
+int launch_opt_fir_warp(const uint8_t *mask, int64_t mpitch, int64_t mstride,
+                        const uint8_t *img, int64_t ipitch, int64_t istride, int C,
+                        uint8_t *rec, int64_t rpitch, int64_t rstride,
+                        int W, int H, int N, int band_h, int wpc, cudaStream_t st);
 
 // record plane: 8 B / pixel, rows padded to whole 4-pixel groups (optimise_ghost.cu reads whole groups)
 size_t optimise_split_rec_bytes(int W, int H, int N)
@@ -816,7 +820,13 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     const bool ghost_iir = iir_sel && !strcmp(iir_sel, "ghost");
     const bool warp_iir = ghost_iir || !iir_sel || strcmp(iir_sel, "cta") != 0;   // both read fmt-1 records
     if (!ghost_iir) iirg_forget(mailbox);
-    {
+    // FIR records: "warp" (default: optimise_firw.cu, fmt 1 only) | "cta" (k_opt_fir below)
+    const char *fir_sel = getenv("B200MRC_FIR");
+    if (warp_iir && (!fir_sel || strcmp(fir_sel, "cta") != 0)) {
+        rc = launch_opt_fir_warp(mask, mpitch, mstride, img, ipitch, istride, C, rec, rpitch, rstride, W, H, N,
+                                 env_int("B200MRC_FIRW_BAND", 256), env_int("B200MRC_FIRW_WPC", 4), st);
+        if (rc != B200MRC_OK) return rc;
+    } else {
         FirParams p;
         p.fmt = warp_iir ? 1 : 0;
         p.mask = mask; p.mpitch = mpitch; p.mstride = mstride; p.img = img; p.ipitch = ipitch; p.istride = istride;
