@@ -99,10 +99,11 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
         if (C == 3) *reinterpret_cast<uint4 *>(myslot + s * 32 * SM::slot) = make_uint4(0, 0, 0, 0);
         else *reinterpret_cast<uint2 *>(myslot + s * 32 * SM::slot) = make_uint2(0, 0);
     }
+    const uint8_t *ii = ip + (int64_t)rmin * p.ipitch, *mm = mp + (int64_t)rmin * p.mpitch;   // next row to copy
+    int ist = 0;                                             // its stage
     auto issue = [&](int i) {                                // streamed row i -> stage i % DEPTH; one commit group per call
         if (i < nrows) {
-            uint8_t *dst = myslot + (i % DEPTH) * 32 * SM::slot;
-            const uint8_t *ii = ip + (int64_t)(rmin + i) * p.ipitch, *mm = mp + (int64_t)(rmin + i) * p.mpitch;
+            uint8_t *dst = myslot + ist * 32 * SM::slot;
             if (acopy) {
                 if (C == 3) { cp_async4(dst, ii); cp_async4(dst + 4, ii + 4); cp_async4(dst + 8, ii + 8); cp_async4(dst + 12, mm); }
                 else { cp_async4(dst, ii); cp_async4(dst + 4, mm); }
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
                     dst[K * C + k] = v ? mm[k] : 0;
                 }
             }
+            ii += p.ipitch; mm += p.mpitch;
+            if (++ist == DEPTH) ist = 0;
         }
         cp_async_commit();
     };
@@ -132,7 +135,10 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
     int o_e9 = slot_of(ys0 + NBG - 1), o_e2 = slot_of(ys0 + NFG - 1), o_cur = slot_of(ys0),
         o_l4 = slot_of(ys0 - NFG - 1), o_l11 = slot_of(ys0 - NBG - 1);
     constexpr int RINW = RIN * 32 * K;
-    int i9 = 0;                                              // streamed index of row y + 9
+    int i9 = 0, cst = 0;                                     // streamed index of row y + 9 and its stage
+    // warp-uniform row history: bit j = the strip's segment of row (y + 9 - j) holds a mask pixel /
+    // holds a pixel that is not a plain bg-layer pixel (mask or outside the page)
+    uint32_t hist_m = 0, hist_x = 0;
 
     for (int y = ys0; y < by1; y++) {
         const int re2 = y + NFG - 1, rl4 = y - NFG - 1, rl11 = y - NBG - 1;
@@ -141,7 +147,8 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
             // ---- row y+9 enters: unpack, flag, keep in the ring, add to the bg sums
             issue(i9 + DEPTH - 1);
             cp_async_wait<DEPTH - 1>();
-            const uint8_t *src = myslot + (i9 % DEPTH) * 32 * SM::slot;
+            const uint8_t *src = myslot + cst * 32 * SM::slot;
+            if (++cst == DEPTH) cst = 0;
             uint32_t mb;
             if (C == 3) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(src);
@@ -160,14 +167,25 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
                 t[0] = perm(v.x, fb, 0x4000); t[1] = perm(v.x, fb, 0x5111); t[2] = perm(v.x, fb, 0x6222); t[3] = perm(v.x, fb, 0x7333);
             }
             *reinterpret_cast<uint4 *>(ring + o_e9 + lane * K) = make_uint4(t[0], t[1], t[2], t[3]);
+            const uint32_t tor = t[0] | t[1] | t[2] | t[3], tand = t[0] & t[1] & t[2] & t[3];
+            hist_m = (hist_m << 1) | (__any_sync(FULL, (int)tor < 0) ? 1u : 0u);
+            hist_x = (hist_x << 1) | (__all_sync(FULL, (tor >> 30) == 1u && ((tand >> 30) & 1u)) ? 0u : 1u);
+            if (!(hist_x & 1u)) {                            // every pixel of the segment is a bg-layer pixel: no flag arithmetic
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const uint32_t m = (t[k] >> 30) & 1u;
-                Fb_rb[k] += lanes_rb(t[k]) * m; Fb_gm[k] += lanes_gm(t[k]) * m;
+                for (int k = 0; k < K; k++) { Fb_rb[k] += lanes_rb(t[k]); Fb_gm[k] += lanes_gm(t[k]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t m = (t[k] >> 30) & 1u;
+                    Fb_rb[k] += lanes_rb(t[k]) * m; Fb_gm[k] += lanes_gm(t[k]) * m;
+                }
             }
             i9++;
+        } else {
+            hist_m <<= 1; hist_x <<= 1;
         }
-        if (re2 >= rmin && re2 < H) {
+        // rows y+2 / y-4 entered 7 / 13 steps ago; rows y-11 entered 20 steps ago
+        if (re2 >= rmin && re2 < H && (hist_m & (1u << 7))) {
             const uint4 v = *reinterpret_cast<const uint4 *>(ring + o_e2 + lane * K);
             t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
 #pragma unroll
@@ -176,7 +194,7 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
                 Ff_rb[k] += lanes_rb(t[k]) * m; Ff_gm[k] += lanes_gm(t[k]) * m;
             }
         }
-        if (rl4 >= rmin) {
+        if (rl4 >= rmin && (hist_m & (1u << 13))) {
             const uint4 v = *reinterpret_cast<const uint4 *>(ring + o_l4 + lane * K);
             t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
 #pragma unroll
@@ -188,18 +206,27 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
         if (rl11 >= rmin) {
             const uint4 v = *reinterpret_cast<const uint4 *>(ring + o_l11 + lane * K);
             t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+            if (!(hist_x & (1u << 20))) {
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const uint32_t m = (t[k] >> 30) & 1u;
-                Fb_rb[k] -= lanes_rb(t[k]) * m; Fb_gm[k] -= lanes_gm(t[k]) * m;
+                for (int k = 0; k < K; k++) { Fb_rb[k] -= lanes_rb(t[k]); Fb_gm[k] -= lanes_gm(t[k]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const uint32_t m = (t[k] >> 30) & 1u;
+                    Fb_rb[k] -= lanes_rb(t[k]) * m; Fb_gm[k] -= lanes_gm(t[k]) * m;
+                }
             }
         }
 
         if (y >= by0) {
             // ---- emit the records of row y
-            const uint4 cv = *reinterpret_cast<const uint4 *>(ring + o_cur + lane * K);
-            const uint32_t cur[K] = {cv.x, cv.y, cv.z, cv.w};
-            const bool need_bg = __any_sync(FULL, real && ((int)(cur[0] | cur[1] | cur[2] | cur[3]) < 0));
+            uint32_t cur[K] = {0, 0, 0, 0};
+            bool need_bg = false;
+            if (hist_m & (1u << 9)) {                        // row y entered 9 steps ago with a mask pixel in the segment
+                const uint4 cv = *reinterpret_cast<const uint4 *>(ring + o_cur + lane * K);
+                cur[0] = cv.x; cur[1] = cv.y; cur[2] = cv.z; cur[3] = cv.w;
+                need_bg = __any_sync(FULL, real && ((int)(cur[0] | cur[1] | cur[2] | cur[3]) < 0));
+            }
             // fg: sum of Ff over [c-3, c+3)
             uint32_t s_rb[K], s_gm[K];
             {
