@@ -318,20 +318,39 @@ class DecomposeBatch:
         return self
 
 
-class StreamedDecomposer:
-    """Host-to-host decomposition of a large batch in chunks: H2D of chunk i+1, the kernels of chunk i
-    and D2H of chunk i-1 run concurrently on three streams over double-buffered device batches, so
-    the PCIe link (full duplex) is the only exposed cost.  Host tensors should be pinned."""
+def _copy2d(dst_ptr, dst_pitch, src_ptr, src_pitch, row_bytes, rows, kind, stream):
+    L.check(L.lib().b200mrc_copy2d(C.c_void_p(dst_ptr), dst_pitch, C.c_void_p(src_ptr), src_pitch, row_bytes, rows, kind,
+                                   C.c_void_p(stream.cuda_stream)), 'b200mrc_copy2d')
 
-    def __init__(self, eng, n_pages, h, w, c, chunk=16, bg_downsample=None, fg_downsample=None, mask_only=False):
+
+class StreamedDecomposer:
+    """Host-to-host decomposition of a large batch in chunks.  H2D of later chunks, the kernels of up to
+    `compute_streams` chunks and D2H of finished chunks run concurrently (copy engines + SMs) over a ring of
+    device batches.  Host<->device transfers are flat 1-D DMAs at full PCIe rate into / out of contiguous device
+    staging; the (un)pitching is a device-to-device b200mrc_copy2d on the compute stream.  Host tensors should be
+    pinned."""
+
+    def __init__(self, eng, n_pages, h, w, c, chunk=4, bg_downsample=None, fg_downsample=None, mask_only=False,
+                 buffers=4, compute_streams=2):
         self.eng, self.n, self.h, self.w, self.c = eng, n_pages, h, w, c
         self.chunk = max(1, min(chunk, n_pages))
-        self.batches = [eng.make_batch(self.chunk, h, w, c, bg_downsample, fg_downsample, mask_only) for _ in range(2)]
+        n_chunks = (n_pages + self.chunk - 1) // self.chunk
+        self.nb = max(1, min(buffers, n_chunks))
+        self.batches = [eng.make_batch(self.chunk, h, w, c, bg_downsample, fg_downsample, mask_only) for _ in range(self.nb)]
         self.mask_only = mask_only
-        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=eng.device) for _ in range(3))
+        self.s_in, self.s_out = torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device)
+        self.s_cmp = [torch.cuda.Stream(device=eng.device) for _ in range(max(1, min(compute_streams, self.nb)))]
         b = self.batches[0]
         self.out_shapes = dict(mask=(h, w), fg=None if mask_only else (b.fg.h, b.fg.w * c), bg=None if mask_only else (b.bg.h, b.bg.w * c))
         self.errors = set(b.errors)
+        # contiguous device staging per buffer (planes whose pitch equals the row length need none)
+        dev = eng.device
+
+        def stage(plane):
+            return None if plane.pitch == plane.w * plane.c else torch.empty((self.chunk, plane.h, plane.w * plane.c), dtype=torch.uint8, device=dev)
+        self.st_in = [stage(b_.img) for b_ in self.batches]
+        self.st_out = [dict(mask=stage(b_.mask), fg=None if mask_only else stage(b_.fg), bg=None if mask_only else stage(b_.bg))
+                       for b_ in self.batches]
 
     def alloc_outputs(self):
         """Pinned host result buffers: mask [N,H,W] u8 (0/1), fg [N,fh,fw*C], bg [N,bh,bw*C]."""
@@ -344,34 +363,46 @@ class StreamedDecomposer:
     def run(self, host_pages, out, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST):
         """host_pages: CPU uint8 tensor [N,H,W(,C)]; out: dict from alloc_outputs().  Returns after
         everything has landed in `out` (one final stream synchronisation)."""
-        n, ck = self.n, self.chunk
+        n, ck, nb = self.n, self.chunk, self.nb
         hp = host_pages.reshape(n, self.h, self.w * self.c)
+        assert hp.is_contiguous() and hp.dtype == torch.uint8
         cur = torch.cuda.current_stream()
-        for s in (self.s_in, self.s_cmp, self.s_out):
+        for s in [self.s_in, self.s_out] + self.s_cmp:
             s.wait_stream(cur)
         in_done, cmp_done, out_done = {}, {}, {}
         n_chunks = (n + ck - 1) // ck
+        names = ('mask',) if self.mask_only else ('mask', 'fg', 'bg')
         for i in range(n_chunks):
             lo, hi = i * ck, min(n, (i + 1) * ck)
             m = hi - lo
-            b = self.batches[i % 2]
+            slot = i % nb
+            b = self.batches[slot]
+            sc = self.s_cmp[i % len(self.s_cmp)]
+            st_in = self.st_in[slot]
             with torch.cuda.stream(self.s_in):
-                if i >= 2:
-                    self.s_in.wait_event(cmp_done[i - 2])          # img buffer of this slot is free again
-                b.img.view()[:m].copy_(hp[lo:hi].to(self.eng.device, non_blocking=True))
+                if i >= nb:
+                    self.s_in.wait_event(cmp_done[i - nb])         # input staging / img plane of this slot is free again
+                (st_in if st_in is not None else b.img.t)[:m].copy_(hp[lo:hi], non_blocking=True)
                 in_done[i] = self.s_in.record_event()
-            with torch.cuda.stream(self.s_cmp):
-                self.s_cmp.wait_event(in_done[i])
-                if i >= 2:
-                    self.s_cmp.wait_event(out_done[i - 2])         # output planes of this slot were drained
+            with torch.cuda.stream(sc):
+                sc.wait_event(in_done[i])
+                if i >= nb:
+                    sc.wait_event(out_done[i - nb])                # output staging of this slot was drained
+                if st_in is not None:
+                    row = self.w * self.c
+                    _copy2d(b.img.t.data_ptr(), b.img.pitch, st_in.data_ptr(), row, row, m * self.h, L.COPY_D2D, sc)
                 b.run(window, k, R, denoise_mask)                  # b200mrc_decompose on the chunk (a short tail chunk recomputes stale pages: harmless)
-                cmp_done[i] = self.s_cmp.record_event()
+                for name in names:
+                    plane, st = getattr(b, name), self.st_out[slot][name]
+                    if st is not None:
+                        row = plane.w * plane.c
+                        _copy2d(st.data_ptr(), row, plane.t.data_ptr(), plane.pitch, row, m * plane.h, L.COPY_D2D, sc)
+                cmp_done[i] = sc.record_event()
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(cmp_done[i])
-                out['mask'][lo:hi].copy_(b.mask.view()[:m], non_blocking=True)
-                if not self.mask_only:
-                    out['fg'][lo:hi].copy_(b.fg.view()[:m], non_blocking=True)
-                    out['bg'][lo:hi].copy_(b.bg.view()[:m], non_blocking=True)
+                for name in names:
+                    plane, st = getattr(b, name), self.st_out[slot][name]
+                    out[name][lo:hi].copy_((st if st is not None else plane.t)[:m], non_blocking=True)
                 out_done[i] = self.s_out.record_event()
         cur.wait_stream(self.s_out)
         self.s_out.synchronize()

@@ -275,7 +275,11 @@ def main():
         from archive_pdf_tools_b200.engine import StreamedDecomposer
         del batch
         torch.cuda.empty_cache()
-        sd = StreamedDecomposer(eng, N, H, W, C, chunk=16, bg_downsample=BG_DS)
+        e2e_chunk = int(os.environ.get('B200MRC_E2E_CHUNK', '4'))
+        e2e_streams = int(os.environ.get('B200MRC_E2E_STREAMS', '2'))
+        e2e_buffers = int(os.environ.get('B200MRC_E2E_BUFFERS', '4'))
+        sd = StreamedDecomposer(eng, N, H, W, C, chunk=e2e_chunk, bg_downsample=BG_DS, buffers=e2e_buffers,
+                                compute_streams=e2e_streams)
         outs = sd.alloc_outputs()
 
         def e2e_step():
@@ -294,8 +298,9 @@ def main():
         e2e = {'value': px_step * e2e_steps / float(dt.item()) / 1e6, 'unit': 'Mpixels/s', 'steps': e2e_steps,
                'h2d_bytes_per_step': int(host.numel()) * world,
                'd2h_bytes_per_step': int(sum(v.numel() for v in outs.values())) * world,
-               'api': 'archive_pdf_tools_b200.engine.StreamedDecomposer.run: pinned host pages -> H2D -> b200mrc_decompose '
-                      '(16-page chunks, 3 streams) -> D2H of mask/fg/bg into pinned host buffers'}
+               'api': 'archive_pdf_tools_b200.engine.StreamedDecomposer.run: pinned host pages -> 1-D H2D DMA -> device pitching '
+                      '(b200mrc_copy2d) -> b200mrc_decompose (%d-page chunks, %d compute streams, %d device buffers) -> device '
+                      'unpitching -> 1-D D2H DMA of mask/fg/bg into pinned host buffers' % (e2e_chunk, e2e_streams, e2e_buffers)}
 
     if rank != 0:
         if world > 1:

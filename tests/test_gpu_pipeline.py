@@ -166,10 +166,34 @@ def test_streamed_decomposer_matches_batched(eng, synth):
     pages = np.stack([synth.make_page(300 + i, 270, 330, dpi=100, sigma_n=3.0, halftone=(i == 2)) for i in range(7)])
     ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
     host = torch.from_numpy(pages).pin_memory()
-    sd = StreamedDecomposer(eng, 7, 270, 330, 3, chunk=2, bg_downsample=3)
-    out = sd.alloc_outputs()
-    for _ in range(2):
-        sd.run(host, out, 25, denoise_mask='fast')
-    assert np.array_equal(out['mask'].numpy().astype(bool), ref['mask'])
-    assert np.array_equal(out['fg'].numpy().reshape(ref['fg'].shape), ref['fg'])
-    assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])
+    for kw in (dict(chunk=2), dict(chunk=2, buffers=2, compute_streams=1), dict(chunk=3, buffers=3, compute_streams=3), dict(chunk=7)):
+        sd = StreamedDecomposer(eng, 7, 270, 330, 3, bg_downsample=3, **kw)
+        out = sd.alloc_outputs()
+        for _ in range(2):
+            for v in out.values():
+                v.zero_()
+            sd.run(host, out, 25, denoise_mask='fast')
+        assert np.array_equal(out['mask'].numpy().astype(bool), ref['mask']), kw
+        assert np.array_equal(out['fg'].numpy().reshape(ref['fg'].shape), ref['fg']), kw
+        assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg']), kw
+
+
+def test_copy2d_roundtrip(eng):
+    """b200mrc_copy2d: pitched H2D / D2D / D2H of a batch of pages keeps every byte, touches no padding."""
+    import ctypes as C
+    import torch
+    from archive_pdf_tools_b200 import _lib, engine as E
+    n, h, w, c = 3, 37, 101, 3
+    src = torch.randint(0, 256, (n, h, w * c), dtype=torch.uint8).pin_memory()
+    a, b = E.Plane(n, h, w, c, eng.device), E.Plane(n, h, w, c, eng.device)
+    a.t.fill_(7); b.t.fill_(9)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L = _lib.lib()
+    assert L.b200mrc_copy2d(a.ptr, a.pitch, C.c_void_p(src.data_ptr()), w * c, w * c, n * h, _lib.COPY_H2D, st) == 0
+    assert L.b200mrc_copy2d(b.ptr, b.pitch, a.ptr, a.pitch, w * c, n * h, _lib.COPY_D2D, st) == 0
+    dst = torch.zeros_like(src).pin_memory()
+    assert L.b200mrc_copy2d(C.c_void_p(dst.data_ptr()), w * c, b.ptr, b.pitch, w * c, n * h, _lib.COPY_D2H, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+    assert bool((b.t[:, :, w * c:] == 9).all())                  # row padding untouched
+    assert L.b200mrc_copy2d(None, 0, None, 0, 1, 1, 1, st) == _lib.ERR_INVALID
