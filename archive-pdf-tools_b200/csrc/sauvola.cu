@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx
     return w;
 }
 
-__global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
+__global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
 {
     // prefix of column sums for the current row, SoA layout, double buffered
     __shared__ uint2 sP[2][SK * (ST + 1)];
@@ -106,16 +106,23 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
     }
 
     // loads run two rows ahead of their use (L2/HBM latency >> one row step): stage A feeds the
-    // next iteration, stage B the one after
+    // next iteration, stage B the one after.  Words are loaded raw through three running row pointers
+    // and masked (columns outside the page read as 0) only when they are consumed, so nothing waits
+    // on a load in the iteration that issues it.
+    const bool lok = gx >= 0 && gx < W;
+    const uint32_t lmask = !lok ? 0u : (W - gx >= 4 ? 0xffffffffu : (1u << (8 * (W - gx))) - 1u);
+    const uint8_t *pe = in + (int64_t)(by0 + 1 + p.u) * p.in_pitch + gx;      // entering row of the next load_upd
+    const uint8_t *pl = in + (int64_t)(by0 + 1 - p.o) * p.in_pitch + gx;      // leaving row
+    const uint8_t *pc = in + (int64_t)(by0 + 1) * p.in_pitch + gx;            // its own pixels
     auto load_upd = [&](int yu, uint32_t &we, uint32_t &wl, uint32_t &wc) {
         // words needed to move the window from row yu-1 to row yu, and row yu's own pixels
         we = 0; wl = 0; wc = 0;
-        if (yu < by1) {
-            const int ye = yu + p.u, yl = yu - p.o;
-            if (ye < H) we = load_word_clamped(in + (int64_t)ye * p.in_pitch, gx, W);
-            if (yl >= 0) wl = load_word_clamped(in + (int64_t)yl * p.in_pitch, gx, W);
-            wc = load_word_clamped(in + (int64_t)yu * p.in_pitch, gx, W);
+        if (yu < by1 && lok) {
+            if (yu + p.u < H) we = __ldg(reinterpret_cast<const uint32_t *>(pe));
+            if (yu - p.o >= 0) wl = __ldg(reinterpret_cast<const uint32_t *>(pl));
+            wc = __ldg(reinterpret_cast<const uint32_t *>(pc));
         }
+        pe += p.in_pitch; pl += p.in_pitch; pc += p.in_pitch;
     };
     uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W);
     uint32_t weA, wlA, wcA, weB, wlB, wcB;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
 
     for (int y = by0; y < by1; y++) {
         const int buf = (y - by0) & 1;
-        const uint32_t wenter = weA, wleave = wlA, wnext = wcA;
+        const uint32_t wenter = weA & lmask, wleave = wlA & lmask, wnext = wcA & lmask;
         weA = weB; wlA = wlB; wcA = wcB;
         load_upd(y + 3, weB, wlB, wcB);
 
@@ -165,27 +172,46 @@ __global__ void __launch_bounds__(ST) k_sauvola_mask(const SauvolaParams p)
             // accurate to 2^-52 relative (a < 2^32, n <= 65025).  The quotients come out as the doubles
             // the test needs, so no int->double conversions of m and v remain.
             if (nx_uniform && ny != ny_cached) { rn_u = 1.0 / (double)(nxv[0] * ny); ny_cached = ny; }
+            if (nx_uniform) {
+                // interior thread: one window area for its 4 pixels (n > 0 because the thread is inside the page)
 #pragma unroll
-            for (int j = 0; j < SK; j++) {
-                const uint2 hi = sP[buf][slot_hi[j]];
-                const uint2 lo = sP[buf][slot_lo[j]];
-                const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
-                const int n = nxv[j] * ny;
-                uint32_t fg = 0;
-                if (n > 0) {
-                    const double rn = nx_uniform ? rn_u : 1.0 / (double)n;
-                    const double md = floor(__dmul_rn(__dadd_rn((double)S, 0.5), rn));      // (double)(S / n)
-                    const double qd = floor(__dmul_rn(__dadd_rn((double)Q, 0.5), rn));      // (double)(Q / n)
-                    const double mm = __dmul_rn(md, md);                                     // exact (integers < 2^53)
+                for (int j = 0; j < SK; j++) {
+                    const uint2 hi = sP[buf][slot_hi[j]];
+                    const uint2 lo = sP[buf][slot_lo[j]];
+                    const double md = floor(__dmul_rn(__dadd_rn((double)(hi.x - lo.x), 0.5), rn_u));   // (double)(S / n)
+                    const double qd = floor(__dmul_rn(__dadd_rn((double)(hi.y - lo.y), 0.5), rn_u));   // (double)(Q / n)
+                    const double mm = __dmul_rn(md, md);                                                // exact (integers < 2^53)
                     const double v = __dadd_rn(qd, -mm);
                     const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
                     const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
                     const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
                     const double lhs = __dmul_rn(t, t);
-                    if (p.kneg) fg = (t <= 0.0) && (lhs >= rhs);
-                    else        fg = (t <= 0.0) || (lhs <= rhs);
+                    const bool fg = p.kneg ? ((t <= 0.0) && (lhs >= rhs)) : ((t <= 0.0) || (lhs <= rhs));
+                    bits |= (fg ? 1u : 0u) << (8 * j);
                 }
-                bits |= fg << (8 * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SK; j++) {
+                    const uint2 hi = sP[buf][slot_hi[j]];
+                    const uint2 lo = sP[buf][slot_lo[j]];
+                    const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
+                    const int n = nxv[j] * ny;
+                    uint32_t fg = 0;
+                    if (n > 0) {
+                        const double rn = 1.0 / (double)n;
+                        const double md = floor(__dmul_rn(__dadd_rn((double)S, 0.5), rn));      // (double)(S / n)
+                        const double qd = floor(__dmul_rn(__dadd_rn((double)Q, 0.5), rn));      // (double)(Q / n)
+                        const double mm = __dmul_rn(md, md);
+                        const double v = __dadd_rn(qd, -mm);
+                        const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
+                        const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
+                        const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
+                        const double lhs = __dmul_rn(t, t);
+                        if (p.kneg) fg = (t <= 0.0) && (lhs >= rhs);
+                        else        fg = (t <= 0.0) || (lhs <= rhs);
+                    }
+                    bits |= fg << (8 * j);
+                }
             }
             if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) bits ^= 0x01010101u;
             uint8_t *orow = out + (int64_t)y * p.out_pitch + gx;
