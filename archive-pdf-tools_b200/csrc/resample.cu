@@ -13,6 +13,8 @@
 // only on the shapes); the kernels are pure gather-multiply-accumulate byte kernels.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 struct b200mrc_resample_plan {
@@ -24,6 +26,10 @@ struct b200mrc_resample_plan {
     int OW, OH, filter;
     int need_h, need_v, ksize_h, ksize_v;
     int *d_bounds_h, *d_kk_h, *d_bounds_v, *d_kk_v;
+    // fused tile path (k_resample_tile): both axes shrink by the same integer factor F with T taps, so every interior
+    // output uses one coefficient row; [ux0,ux1) x [uy0,uy1) are the outputs that do
+    int tile_F, tile_T, offx, offy, ux0, ux1, uy0, uy1;
+    int kh[16], kv[16];
 };
 
 namespace b200mrc {
@@ -160,6 +166,150 @@ __global__ void __launch_bounds__(256) k_resample_v(const ResampleParams p)
         for (int j = 0; j < 4 && b4 + j < nb; j++) dst[j] = (uint8_t)(o >> (8 * j));
 }
 
+// ---- fused horizontal + vertical pass for integer shrink factors (the production bg/3 thumbnail) ----------------
+// One CTA produces a TOW x TOH output tile: the horizontal pass of the F*TOH+T-F input rows it needs goes into
+// shared memory (uint8, exactly Pillow's intermediate), the vertical pass reads it back.  Interior outputs all use
+// the same T coefficients, which sit in the kernel's constant bank; a thread of the horizontal pass loads the
+// (3F+T)*C input bytes of 4 adjacent outputs as aligned words once and extracts every byte once.  Tiles that
+// touch the image border (clipped, renormalised windows) take the table-driven form of the same arithmetic.
+constexpr int TOW = 32, TOH = 16;
+
+struct TileParams {
+    const uint8_t *in; int64_t in_pitch, in_stride;
+    uint8_t *out; int64_t out_pitch, out_stride;
+    int in_w, in_h, out_w, out_h, ksize_h, ksize_v;
+    const int *bounds_h, *kk_h, *bounds_v, *kk_v;
+    int offx, offy, ux0, ux1, uy0, uy1;
+    int kh[16], kv[16];
+};
+
+template <int C, int F, int T>
+__global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
+{
+    constexpr int RMAX = F * TOH + T, HROW = TOW * C;
+    __shared__ __align__(16) uint8_t hbuf[RMAX * HROW];
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * TOW, oy0 = blockIdx.y * TOH, page = blockIdx.z;
+    const int ow = min(TOW, p.out_w - ox0), oh = min(TOH, p.out_h - oy0);
+    const int ylast = oy0 + oh - 1;
+    const int ry0 = p.bounds_v[2 * oy0], rows_in = p.bounds_v[2 * ylast] + p.bounds_v[2 * ylast + 1] - ry0;
+    const bool ux = ox0 >= p.ux0 && ox0 + ow <= p.ux1, uy = oy0 >= p.uy0 && oy0 + oh <= p.uy1;
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride + (int64_t)ry0 * p.in_pitch;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride + (int64_t)oy0 * p.out_pitch + (int64_t)ox0 * C;
+
+    auto generic_h = [&](int r, int oxl) {                    // one output pixel of input row ry0 + r
+        const int ox = ox0 + oxl, xmin = p.bounds_h[2 * ox], cnt = p.bounds_h[2 * ox + 1];
+        const int *k = p.kk_h + (size_t)ox * p.ksize_h;
+        const uint8_t *q = in + (int64_t)r * p.in_pitch + (int64_t)xmin * C;
+        int acc[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[c] = 1 << 21;
+        for (int i = 0; i < cnt; i++) {
+            const int kv = __ldg(k + i);
+#pragma unroll
+            for (int c = 0; c < C; c++) acc[c] += (int)q[i * C + c] * kv;
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) hbuf[r * HROW + oxl * C + c] = clip8(acc[c]);
+    };
+    // ---- horizontal pass
+    const int ngrp = ux ? ow / 4 : 0;
+    if (ngrp > 0) {
+        constexpr int NB = (3 * F + T) * C, NW = (NB + 3) / 4;
+        for (int task = tid; task < rows_in * ngrp; task += 256) {
+            const int r = task / ngrp, g = task - r * ngrp;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (int64_t)r * p.in_pitch + (int64_t)(F * (ox0 + 4 * g) + p.offx) * C);
+            uint32_t w[NW];
+#pragma unroll
+            for (int i = 0; i < NW; i++) w[i] = __ldg(src + i);
+            int acc[4][C];
+#pragma unroll
+            for (int px = 0; px < 4; px++)
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[px][c] = 1 << 21;
+#pragma unroll
+            for (int px = 0; px < 4; px++)
+#pragma unroll
+                for (int t = 0; t < T; t++)
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int b = (px * F + t) * C + c;
+                        acc[px][c] += (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu) * p.kh[t];
+                    }
+            uint32_t ow_[C];                                  // 4*C output bytes = C words
+#pragma unroll
+            for (int i = 0; i < C; i++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const int b = 4 * i + j; v |= (uint32_t)clip8(acc[b / C][b % C]) << (8 * j); }
+                ow_[i] = v;
+            }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(hbuf + r * HROW + 4 * g * C);
+#pragma unroll
+            for (int i = 0; i < C; i++) dst[i] = ow_[i];
+        }
+    }
+    {
+        const int rest = ow - 4 * ngrp;                       // pixels not covered by whole groups
+        for (int task = tid; task < rows_in * rest; task += 256) {
+            const int r = task / rest;
+            generic_h(r, 4 * ngrp + (task - r * rest));
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass: one thread per 4 output bytes
+    const int nb = ow * C, nwords = (nb + 3) / 4;
+    for (int task = tid; task < oh * nwords; task += 256) {
+        const int oy = task / nwords, b4 = 4 * (task - oy * nwords);
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
+        if (uy) {
+            const uint8_t *q = hbuf + (F * (oy0 + oy) + p.offy - ry0) * HROW + b4;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(q + t * HROW);
+                const int kv = p.kv[t];
+                a0 += (int)(w & 0xffu) * kv; a1 += (int)((w >> 8) & 0xffu) * kv; a2 += (int)((w >> 16) & 0xffu) * kv; a3 += (int)(w >> 24) * kv;
+            }
+        } else {
+            const int yy = oy0 + oy, cnt = p.bounds_v[2 * yy + 1];
+            const int *k = p.kk_v + (size_t)yy * p.ksize_v;
+            const uint8_t *q = hbuf + (p.bounds_v[2 * yy] - ry0) * HROW + b4;
+            for (int i = 0; i < cnt; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(q + i * HROW);
+                const int kv = __ldg(k + i);
+                a0 += (int)(w & 0xffu) * kv; a1 += (int)((w >> 8) & 0xffu) * kv; a2 += (int)((w >> 16) & 0xffu) * kv; a3 += (int)(w >> 24) * kv;
+            }
+        }
+        const uint32_t o = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
+        uint8_t *dst = out + (int64_t)oy * p.out_pitch + b4;
+        if (b4 + 3 < nb) *reinterpret_cast<uint32_t *>(dst) = o;
+        else
+            for (int j = 0; b4 + j < nb; j++) dst[j] = (uint8_t)(o >> (8 * j));
+    }
+}
+
+// the interior of a coefficient table: outputs [lo, hi) whose window is bounds = F*i + off with the same T weights
+void find_uniform(const std::vector<int> &bounds, const std::vector<int> &kk, int ksize, int outSize,
+                  int &F, int &T, int &off, int &lo, int &hi, int *kout)
+{
+    F = T = off = lo = hi = 0;
+    if (outSize < 4) return;
+    const int mid = outSize / 2;
+    T = bounds[2 * mid + 1];
+    F = bounds[2 * (mid + 1)] - bounds[2 * mid];
+    off = bounds[2 * mid] - F * mid;
+    if (T < 1 || T > 16 || F < 1) { F = 0; return; }
+    auto same = [&](int i) {
+        if (bounds[2 * i] != F * i + off || bounds[2 * i + 1] != T) return false;
+        for (int t = 0; t < T; t++) if (kk[(size_t)i * ksize + t] != kk[(size_t)mid * ksize + t]) return false;
+        return true;
+    };
+    lo = mid; hi = mid + 1;
+    while (lo > 0 && same(lo - 1)) lo--;
+    while (hi < outSize && same(hi)) hi++;
+    for (int t = 0; t < 16; t++) kout[t] = t < T ? kk[(size_t)mid * ksize + t] : 0;
+}
+
 struct ReduceParams {
     const uint8_t *in; int64_t in_pitch, in_stride;
     uint8_t *out; int64_t out_pitch, out_stride;
@@ -263,6 +413,14 @@ extern "C" b200mrc_resample_plan *b200mrc_thumbnail_plan_create(int width, int h
     std::vector<int> bh, kh, bv, kv;
     pl->ksize_h = build_coeffs(pl->SW, pl->bx0, pl->bx1, OW, filter, bh, kh);
     pl->ksize_v = build_coeffs(pl->SH, pl->by0, pl->by1, OH, filter, bv, kv);
+    {
+        int Fh, Th, Fv, Tv;
+        find_uniform(bh, kh, pl->ksize_h, OW, Fh, Th, pl->offx, pl->ux0, pl->ux1, pl->kh);
+        find_uniform(bv, kv, pl->ksize_v, OH, Fv, Tv, pl->offy, pl->uy0, pl->uy1, pl->kv);
+        const bool ok = pl->fx == 1 && pl->fy == 1 && pl->need_h && pl->need_v && Fh == Fv && Th == Tv && Fh == 3 && Th == 12 &&
+                        ((pl->offx * channels) & 3) == 0 && pl->ux1 - pl->ux0 >= TOW && pl->uy1 - pl->uy0 >= TOH;
+        pl->tile_F = ok ? Fh : 0; pl->tile_T = ok ? Th : 0;
+    }
     int rc = upload(bh, &pl->d_bounds_h);
     if (!rc) rc = upload(kh, &pl->d_kk_h);
     if (!rc) rc = upload(bv, &pl->d_bounds_v);
@@ -328,6 +486,21 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         for (int n = 0; n < n_pages; n++)
             B200MRC_CUDA_TRY(cudaMemcpy2DAsync(out + (int64_t)n * out_page_stride, out_pitch, src + (int64_t)n * src_stride, src_pitch,
                                                (size_t)pl->OW * pl->C, (size_t)pl->OH, cudaMemcpyDeviceToDevice, st));
+        return B200MRC_OK;
+    }
+    if (pl->tile_F == 3 && pl->tile_T == 12 && !(src_pitch & 3) && !(src_stride & 3) && !((uintptr_t)src & 3) &&
+        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, TOH) <= 65535 && !getenv("B200MRC_RESAMPLE_2PASS")) {
+        TileParams t;
+        t.in = src; t.in_pitch = src_pitch; t.in_stride = src_stride; t.out = out; t.out_pitch = out_pitch; t.out_stride = out_page_stride;
+        t.in_w = pl->SW; t.in_h = pl->SH; t.out_w = pl->OW; t.out_h = pl->OH; t.ksize_h = pl->ksize_h; t.ksize_v = pl->ksize_v;
+        t.bounds_h = pl->d_bounds_h; t.kk_h = pl->d_kk_h; t.bounds_v = pl->d_bounds_v; t.kk_v = pl->d_kk_v;
+        t.offx = pl->offx; t.offy = pl->offy; t.ux0 = pl->ux0; t.ux1 = pl->ux1; t.uy0 = pl->uy0; t.uy1 = pl->uy1;
+        memcpy(t.kh, pl->kh, sizeof(t.kh)); memcpy(t.kv, pl->kv, sizeof(t.kv));
+        dim3 grid(cdiv(pl->OW, TOW), cdiv(pl->OH, TOH), n_pages);
+        { ProfScope _ps("k_resample_tile", st);
+          if (pl->C == 1) k_resample_tile<1, 3, 12><<<grid, 256, 0, st>>>(t);
+          else k_resample_tile<3, 3, 12><<<grid, 256, 0, st>>>(t); }
+        B200MRC_LAUNCH_CHECK();
         return B200MRC_OK;
     }
     if (pl->need_h) {
