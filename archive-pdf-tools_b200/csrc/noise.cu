@@ -16,6 +16,7 @@
 //                    so an even count reproduces np.median's float32 mean of two.
 #include "common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace b200mrc {
 namespace {
@@ -69,6 +70,62 @@ __global__ void __launch_bounds__(256) k_noise_dd(const NoiseParams p)
     p.keys[(int64_t)page * stride + (int64_t)yo * p.ow + xo] = key;
     if (yo == p.oh - 1 && xo == p.ow - 1)
         for (int64_t q = (int64_t)p.oh * p.ow; q < stride; q++) p.keys[(int64_t)page * stride + q] = 0u;
+}
+
+
+// Separable marching form of k_noise_dd: a warp owns 31 output columns (lane 0 is a ghost that only supplies the
+// left neighbour's pair) and marches down a band of output rows.  Every lane keeps the gray values of its two input
+// columns for the 4 rows of the vertical filter in registers (2 new rows per step, each pixel converted once),
+// computes the two vertical results exactly like k_noise_dd and takes the other two from its left neighbour by
+// shuffle.  Same float32 operations in the same order as k_noise_dd, ~7x fewer instructions.
+constexpr int DD_BAND = 32;
+
+__global__ void __launch_bounds__(128) k_noise_dd_march(const NoiseParams p)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xo = (blockIdx.x * 4 + wid) * 31 + lane - 1;            // lane 0: ghost column pair of xo0 - 1
+    const int yo0 = blockIdx.y * DD_BAND, yo1 = min(p.oh, yo0 + DD_BAND);
+    const int page = blockIdx.z;
+    if ((blockIdx.x * 4 + wid) * 31 >= p.ow) return;
+    const float f0 = (float)-0.48296291314469025, f1 = (float)0.836516303737469,
+                f2 = (float)-0.22414386804185735, f3 = (float)-0.12940952255092145;
+    const int h = p.he - p.hs, w = p.we - p.ws;
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    // this lane's two source columns: taps j2 = 1 (2xo) and j2 = 0 (2xo + 1); xo may be -1 (ghost) or >= ow (idle)
+    const int64_t ca = (int64_t)(p.ws + sym_idx(2 * xo, w)) * p.C, cb = (int64_t)(p.ws + sym_idx(2 * xo + 1, w)) * p.C;
+    auto gray2 = [&](int row, float &ga, float &gb) {
+        const uint8_t *r = in + (int64_t)row * p.in_pitch;
+        uint32_t a, b;
+        if (p.C == 1) { a = r[ca]; b = r[cb]; }
+        else { a = luma_l24(r[ca], r[ca + 1], r[ca + 2]); b = luma_l24(r[cb], r[cb + 1], r[cb + 2]); }
+        ga = __int_as_float(0x4B000000 | a) - 8388608.0f;            // exact (float)a for a < 2^23, no conversion unit
+        gb = __int_as_float(0x4B000000 | b) - 8388608.0f;
+    };
+    // rows of the vertical taps j = 0..3 are 2yo+1, 2yo, 2yo-1, 2yo-2 (symmetric extension)
+    int pr0 = -1, pr1 = -1;                                           // rows held in (a0,b0) / (a1,b1) from the previous step
+    float a0 = 0, b0 = 0, a1 = 0, b1 = 0, a2, b2, a3, b3;
+    const int64_t stride = ((int64_t)p.oh * p.ow + 3) & ~3ll;
+    for (int yo = yo0; yo < yo1; yo++) {
+        const int r0 = p.hs + sym_idx(2 * yo + 1, h), r1 = p.hs + sym_idx(2 * yo, h),
+                  r2 = p.hs + sym_idx(2 * yo - 1, h), r3 = p.hs + sym_idx(2 * yo - 2, h);
+        if (r2 == pr0 && r3 == pr1) { a2 = a0; b2 = b0; a3 = a1; b3 = b1; }   // the usual case: slide by two rows
+        else { gray2(r2, a2, b2); gray2(r3, a3, b3); }
+        gray2(r0, a0, b0); gray2(r1, a1, b1);
+        pr0 = r0; pr1 = r1;
+        float da = 0.0f, db = 0.0f;
+        da = __fadd_rn(da, __fmul_rn(f0, a0)); da = __fadd_rn(da, __fmul_rn(f1, a1)); da = __fadd_rn(da, __fmul_rn(f2, a2)); da = __fadd_rn(da, __fmul_rn(f3, a3));
+        db = __fadd_rn(db, __fmul_rn(f0, b0)); db = __fadd_rn(db, __fmul_rn(f1, b1)); db = __fadd_rn(db, __fmul_rn(f2, b2)); db = __fadd_rn(db, __fmul_rn(f3, b3));
+        // horizontal taps j2 = 0..3: columns 2xo+1 (db), 2xo (da), 2xo-1 (left db), 2xo-2 (left da)
+        const float lb = __shfl_up_sync(0xffffffffu, db, 1), la = __shfl_up_sync(0xffffffffu, da, 1);
+        float dd = 0.0f;
+        dd = __fadd_rn(dd, __fmul_rn(f0, db)); dd = __fadd_rn(dd, __fmul_rn(f1, da)); dd = __fadd_rn(dd, __fmul_rn(f2, lb)); dd = __fadd_rn(dd, __fmul_rn(f3, la));
+        if (lane >= 1 && xo < p.ow) {
+            const uint32_t key = dd == 0.0f ? 0u : (__float_as_uint(dd) & 0x7fffffffu);
+            p.keys[(int64_t)page * stride + (int64_t)yo * p.ow + xo] = key;
+            if (yo == p.oh - 1 && xo == p.ow - 1)
+                for (int64_t q = (int64_t)p.oh * p.ow; q < stride; q++) p.keys[(int64_t)page * stride + q] = 0u;
+        }
+    }
 }
 
 constexpr int SEL_T = 1024;
@@ -238,8 +295,13 @@ int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride
     p.oh = (p.he - p.hs + 3) / 2; p.ow = (p.we - p.ws + 3) / 2;
     p.keys = (uint32_t *)workspace;
     p.sigma_out = sigma_out;
-    dim3 grid(cdiv(p.ow, 32), cdiv(p.oh, 8), N);
-    { ProfScope _ps("k_noise_dd", st); k_noise_dd<<<grid, 256, 0, st>>>(p); }
+    if (getenv("B200MRC_NOISE_DIRECT")) {
+        dim3 grid(cdiv(p.ow, 32), cdiv(p.oh, 8), N);
+        { ProfScope _ps("k_noise_dd", st); k_noise_dd<<<grid, 256, 0, st>>>(p); }
+    } else {
+        dim3 grid(cdiv(p.ow, 4 * 31), cdiv(p.oh, DD_BAND), N);
+        { ProfScope _ps("k_noise_dd_march", st); k_noise_dd_march<<<grid, 128, 0, st>>>(p); }
+    }
     B200MRC_LAUNCH_CHECK();
     { ProfScope _ps("k_noise_select", st); k_noise_select<<<N, SEL_T, 0, st>>>(p); }
     B200MRC_LAUNCH_CHECK();
