@@ -32,7 +32,7 @@ DISTINCT_PAGES = 16                    # generated per rank; tiled to the 64-pag
 METRIC = 'MRC decompose Mpixels/sec @400-DPI pages (64 RGB pages 3300x2550 per GPU, bg/3, denoise fast)'
 WORKLOAD = 'configs[1]: batch 64 RGB pages 3300x2550 @400 DPI, full MRC decompose, bg-downsample=3'
 BYTES_PER_PX_PIPELINE = 3 + 1 + 3 + 3.0 / 9           # 7.333 B/px
-BYTES_PER_PX_OPTIMISE = 3 + 1 + 3 + 3                 # optimise stage (k_opt_fir + k_opt_iir): img + mask in, fg + bg out
+BYTES_PER_PX_OPTIMISE = 3 + 1 + 3 + 3                 # optimise stage (k_opt_fir_w + k_opt_iir_w): img + mask in, fg + bg out
 
 
 def _gen_page(idx):
@@ -323,7 +323,7 @@ def main():
                 'frac': achieved / peak if achieved else None, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_px': BYTES_PER_PX_OPTIMISE, 'kernel_ms': dom_ms,
                 'note': 'algorithmic bytes = the optimise stage (img 3 + mask 1 in, fg 3 + bg 3 out) x pixels per launch; '
-                        'the stage is k_opt_fir + k_opt_iir, frac_stage uses both',
+                        'the stage is k_opt_fir_w + k_opt_iir_w (the sweep that completes it is the dominant kernel), frac_stage uses both',
                 'frac_stage': (BYTES_PER_PX_OPTIMISE * N * H * W / (opt_ms / 1e3) / 1e9 / peak) if opt_ms else None,
                 'pipeline_frac': BYTES_PER_PX_PIPELINE * N * H * W / (dev_ms / args.steps / 1e3) / 1e9 / peak,
                 'kernel_ms_all': kernel_ms, 'stage_ms': stage_ms}
