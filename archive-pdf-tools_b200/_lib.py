@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libb200mrc.so')
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_ALIGNMENT = 0, -1, -2, -3, -4
-SAUVOLA_OR_INTO, SAUVOLA_RAW_INVERTED = 1, 2
+SAUVOLA_OR_INTO, SAUVOLA_RAW_INVERTED, SAUVOLA_INVERT_INPUT = 1, 2, 4
 DECOMPOSE_DENOISE_FAST, DECOMPOSE_MASK_ONLY, DECOMPOSE_NO_NOISE_EST = 1, 2, 4
 MAX_WINDOW, MAX_OPT_N = 255, 16
 COPY_H2D, COPY_D2H, COPY_D2D = 1, 2, 3
@@ -18,6 +18,10 @@ COPY_H2D, COPY_D2H, COPY_D2D = 1, 2, 3
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 i64 = C.c_int64
+
+
+class Rect(C.Structure):
+    _fields_ = [('ptr', vp), ('pitch', i64), ('width', C.c_int32), ('height', C.c_int32), ('keys', vp)]
 
 
 class DecomposeArgs(C.Structure):
@@ -60,6 +64,8 @@ PROTOTYPES = {
     'b200mrc_resample_plan_out_size': (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'b200mrc_resample_workspace_bytes': (C.c_size_t, [vp, C.c_int]),
     'b200mrc_resample': (C.c_int, [vp, vp, i64, i64, vp, i64, i64, C.c_int, vp, C.c_size_t, vp]),
+    'b200mrc_rects_count_nonzero': (C.c_int, [vp, C.c_int, vp, vp]),
+    'b200mrc_rects_sigma_bool': (C.c_int, [vp, C.c_int, vp, vp]),
     'b200mrc_channel_stats': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
     'b200mrc_special_gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     'b200mrc_decompose_workspace_bytes': (C.c_size_t, [C.POINTER(DecomposeArgs)]),

@@ -39,11 +39,11 @@ struct SauvolaParams {
     int kneg, flags;
 };
 
-__device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx, int W)
+__device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx, int W, uint32_t inv)
 {
-    // 4 pixels gx..gx+3 (gx % 4 == 0); pixels outside [0, W) read as 0
+    // 4 pixels gx..gx+3 (gx % 4 == 0), optionally inverted (255 - p); pixels outside [0, W) read as 0
     if (gx < 0 || gx >= W) return 0u;
-    uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+    uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row + gx)) ^ inv;
     int valid = W - gx;                  // >= 1
     if (valid < 4) w &= (1u << (8 * valid)) - 1u;
     return w;
@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
     const int gx = ex0 + i0;                      // global column (multiple of 4, may be < 0 or >= W)
     const bool is_out = (gx >= sx0) && (gx < sx0 + p.strip_w) && (gx < W);
 
+    const uint32_t inv = (p.flags & B200MRC_SAUVOLA_INVERT_INPUT) ? 0xffffffffu : 0u;   // threshold 255 - p (mrc.py:226)
     uint32_t cs[SK], cq[SK];
 #pragma unroll
     for (int j = 0; j < SK; j++) { cs[j] = 0; cq[j] = 0; }
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
     {
         const int r0 = max(0, by0 - p.o + 1), r1 = min(H - 1, by0 + p.u);
         for (int yy = r0; yy <= r1; yy++) {
-            uint32_t w = load_word_clamped(in + (int64_t)yy * p.in_pitch, gx, W);
+            uint32_t w = load_word_clamped(in + (int64_t)yy * p.in_pitch, gx, W, inv);
 #pragma unroll
             for (int j = 0; j < SK; j++) {
                 uint32_t v = (w >> (8 * j)) & 0xFFu;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
         }
         pe += p.in_pitch; pl += p.in_pitch; pc += p.in_pitch;
     };
-    uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W);
+    uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W, inv);
     uint32_t weA, wlA, wcA, weB, wlB, wcB;
     load_upd(by0 + 1, weA, wlA, wcA);
     load_upd(by0 + 2, weB, wlB, wcB);
@@ -133,7 +134,10 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
 
     for (int y = by0; y < by1; y++) {
         const int buf = (y - by0) & 1;
-        const uint32_t wenter = weA & lmask, wleave = wlA & lmask, wnext = wcA & lmask;
+        // rows outside the page were not loaded (0) and must stay 0 under inversion
+        const uint32_t inv_e = (y + 1 + p.u < H && y + 1 < by1) ? inv : 0u, inv_l = (y + 1 - p.o >= 0 && y + 1 < by1) ? inv : 0u,
+                       inv_c = (y + 1 < by1) ? inv : 0u;
+        const uint32_t wenter = (weA ^ inv_e) & lmask, wleave = (wlA ^ inv_l) & lmask, wnext = (wcA ^ inv_c) & lmask;
         weA = weB; wlA = wlB; wcA = wcB;
         load_upd(y + 3, weB, wlB, wcB);
 

@@ -49,20 +49,131 @@ def _sync_time(t0):
     return time() - t0
 
 
+def _hocr_choice(ratio, inv_ratio, sigmas):
+    """The polarity rule of mrc.py:238-263: 0 = leave the mask alone, 1 = thres, 2 = thres_invert."""
+    if ratio < 0.3 or inv_ratio < 0.3:
+        if inv_ratio > 0.2 and ratio < 0.2:
+            return 1
+        ratio_sigma, inv_ratio_sigma = sigmas
+        # Prefer ratio over inv_ratio by a bit
+        if inv_ratio < 0.3 and inv_ratio < ratio and \
+                (inv_ratio_sigma < ratio_sigma or (ratio_sigma < 0.1 and inv_ratio_sigma < 0.1)):
+            return 2
+        elif ratio < 0.2:
+            return 1
+    return 0
+
+
+def _needs_sigma(ratio, inv_ratio):
+    return (ratio < 0.3 or inv_ratio < 0.3) and not (inv_ratio > 0.2 and ratio < 0.2)
+
+
 def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, timing_data=None):
-    """mrc.py:188-270.  Per text line: Sauvola (k=0.1) on the crop and on the inverted crop, pick
-    the polarity by fill ratio.  The estimate_sigma tie-break on boolean crops (mrc.py:253-254)
-    is the not-yet-built part of SURVEY.md section 8(f)1."""
+    """mrc.py:188-270 on the device.  img: gray Plane (the plain 'L' page, n = 1); mask_arr: mask Plane, modified in
+    place.  Per text line: Sauvola (k = 0.1) on the crop and on the inverted crop, polarity picked by fill ratio and,
+    for the undecided lines, by mean_estimate_sigma of the two boolean results; the winner is pasted into the mask.
+    All lines of the page go through the device together: 3 small launches per line, then one count kernel, one
+    sigma kernel and the pastes (in line order, so overlapping boxes resolve like the reference's loop); the host
+    only takes the per-line decisions (two small D2H reads per page)."""
+    import ctypes as C
+    import sys
     t = time()
-    found = False
-    for paragraph in hocr_word_data:
-        for line in paragraph['lines']:
-            found = True
-    if found:
-        raise NotImplementedError('hOCR line masks (mrc.py:188-270) are the next row of the hot-path scope '
-                                  '(SURVEY.md section 8f); pass hocr_word_data=[] for now')
+    lines = []
+    if hocr_word_data:
+        image_width, image_height = img.w, img.h
+        for paragraph in hocr_word_data:
+            for line in paragraph['lines']:
+                coords = line['bbox']
+                line_text = ' '.join([word['text'] for word in line['words']])
+                line_confs = [word['confidence'] for word in line['words']]
+                line_conf = sum(line_confs) / len(line_confs) if len(line_confs) else 0
+                if line_text.strip() == '' or line_conf < 20:
+                    continue
+                if downsample is not None:
+                    coords = [int(x / downsample) for x in coords]
+                else:
+                    coords = [int(x) for x in coords]
+                left, top, right, bottom = coords
+                # This can happen if we downsample and round to int
+                if left == right or top == bottom:
+                    continue
+                if (left >= right) or (top >= bottom):
+                    print('Invalid bounding box: (%d, %d, %d, %d)' % (left, top, right, bottom), file=sys.stderr)
+                    continue
+                if (left < 0) or (right > image_width) or (top < 0) or (bottom > image_height):
+                    print('Invalid bounding box outside image: (%d, %d, %d, %d)' % (left, top, right, bottom), file=sys.stderr)
+                    continue
+                lines.append((left, top, right, bottom))
+    if lines:
+        eng = get_engine()
+        lib = L.lib()
+        st = E._stream_ptr()
+        window = E.window_for_dpi(dpi)
+        k = 0.1          # XXX (reference): If you tweak k, you must tweak the various ratio and sigma's
+        # one scratch buffer: per line an aligned copy of the crop and the two threshold results
+        geo, off = [], 0
+        for (left, top, right, bottom) in lines:
+            w, h = right - left, bottom - top
+            pitch = (w + 15) // 16 * 16
+            size = (pitch * h + 255) // 256 * 256
+            geo.append((w, h, pitch, off, off + size, off + 2 * size))
+            off += 3 * size
+        scratch = torch.empty(off, dtype=torch.uint8, device=eng.device)
+        base = scratch.data_ptr()
+        for (left, top, right, bottom), (w, h, pitch, o_in, o_th, o_ti) in zip(lines, geo):
+            L.check(lib.b200mrc_copy2d(C.c_void_p(base + o_in), pitch, C.c_void_p(img.t.data_ptr() + top * img.pitch + left), img.pitch,
+                                       w, h, L.COPY_D2D, st), 'b200mrc_copy2d')
+            for o_out, flags in ((o_th, 0), (o_ti, L.SAUVOLA_INVERT_INPUT)):
+                L.check(lib.b200mrc_sauvola(C.c_void_p(base + o_in), pitch, pitch * h, C.c_void_p(base + o_out), pitch, pitch * h,
+                                            w, h, 1, window, window, k, 128.0, flags, st), 'b200mrc_sauvola')
+
+        def rects(items):                                    # items: (ptr, pitch, w, h, keys_ptr)
+            arr = (L.Rect * len(items))()
+            for r, (ptr, pitch, w, h, keys) in zip(arr, items):
+                r.ptr, r.pitch, r.width, r.height, r.keys = ptr, pitch, w, h, keys
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            return host.to(eng.device)
+
+        items = []
+        for (w, h, pitch, o_in, o_th, o_ti) in geo:
+            items += [(base + o_th, pitch, w, h, 0), (base + o_ti, pitch, w, h, 0)]
+        rd = rects(items)
+        counts = torch.empty(len(items), dtype=torch.int32, device=eng.device)
+        L.check(lib.b200mrc_rects_count_nonzero(C.c_void_p(rd.data_ptr()), len(items), C.c_void_p(counts.data_ptr()), st),
+                'b200mrc_rects_count_nonzero')
+        counts = counts.cpu().tolist()
+        ratios = []
+        for i, (w, h, *_r) in enumerate(geo):
+            size = w * h
+            ones, ones_i = counts[2 * i], counts[2 * i + 1]
+            ratios.append((ones / ((size - ones) + ones), ones_i / ((size - ones_i) + ones_i)))
+        need = [i for i, (r, ri) in enumerate(ratios) if _needs_sigma(r, ri)]
+        sig = {}
+        if need:
+            koff, kitems = 0, []
+            for i in need:
+                w, h, pitch, o_in, o_th, o_ti = geo[i]
+                nk = ((h + 3) // 2) * ((w + 3) // 2) * 8
+                kitems += [(base + o_th, pitch, w, h, koff), (base + o_ti, pitch, w, h, koff + nk)]
+                koff += 2 * nk
+            keys = torch.empty(max(koff, 8), dtype=torch.uint8, device=eng.device)
+            kitems = [(p_, pi, w, h, keys.data_ptr() + ko) for (p_, pi, w, h, ko) in kitems]
+            kd = rects(kitems)
+            sg = torch.empty(len(kitems), dtype=torch.float64, device=eng.device)
+            L.check(lib.b200mrc_rects_sigma_bool(C.c_void_p(kd.data_ptr()), len(kitems), C.c_void_p(sg.data_ptr()), st),
+                    'b200mrc_rects_sigma_bool')
+            sg = sg.cpu().tolist()
+            for j, i in enumerate(need):
+                sig[i] = (sg[2 * j], sg[2 * j + 1])
+        for i, ((left, top, right, bottom), (w, h, pitch, o_in, o_th, o_ti)) in enumerate(zip(lines, geo)):
+            c = _hocr_choice(ratios[i][0], ratios[i][1], sig.get(i))
+            if c:
+                L.check(lib.b200mrc_copy2d(C.c_void_p(mask_arr.t.data_ptr() + top * mask_arr.pitch + left), mask_arr.pitch,
+                                           C.c_void_p(base + (o_th if c == 1 else o_ti)), pitch, w, h, L.COPY_D2D, st), 'b200mrc_copy2d')
+        torch.cuda.current_stream().synchronize()           # scratch buffers stay alive until the pastes are done
     if timing_data is not None:
         timing_data.append(('hocr_mask_gen', time() - t))
+    return len(lines)
 
 
 def create_mrc_hocr_components(image, hocr_word_data,
@@ -95,12 +206,21 @@ def create_mrc_hocr_components(image, hocr_word_data,
         timing_data.append(('grey_conversion', time() - t))
 
     mask = E.Plane(1, height_, width_, 1, eng.device)
-    create_hocr_mask(None, None, hocr_word_data, downsample=downsample, dpi=dpi, timing_data=timing_data)
-
     if page is not None:
         src = E.Plane(1, height_, width_, page.shape[2] if page.ndim == 3 else 1, eng.device).upload(page[None])
     else:
         src = E.Plane(1, height_, width_, 1, eng.device).upload(gray_host[None])
+
+    # ---- hOCR line masks (mrc.py:367-370) on the plain gray page
+    n_lines = 0
+    if hocr_word_data:
+        mask.t.zero_()                                       # mask_arr = np.array(Image.new('1', size))
+        gray_plain = src if src.c == 1 else E.Plane(1, height_, width_, 1, eng.device)
+        if src.c != 1:
+            eng.gray_blur(src, gray_plain, None)
+        n_lines = create_hocr_mask(gray_plain, mask, hocr_word_data, downsample=downsample, dpi=dpi, timing_data=timing_data)
+    elif timing_data is not None:
+        timing_data.append(('hocr_mask_gen', 0.0))
 
     # ---- create_threshold_mask (mrc.py:300-329)
     t = time()
@@ -117,7 +237,7 @@ def create_mrc_hocr_components(image, hocr_word_data,
     else:
         eng.gray_blur(src, gray, None)
     t = time()
-    eng.sauvola(gray, mask, E.window_for_dpi(dpi), k=0.34, R=128.0)
+    eng.sauvola(gray, mask, E.window_for_dpi(dpi), k=0.34, R=128.0, flags=L.SAUVOLA_OR_INTO if n_lines else 0)   # mask_arr |= thres_arr
     if timing_data is not None:
         timing_data.append(('threshold', _sync_time(t)))
 

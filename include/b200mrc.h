@@ -53,6 +53,7 @@ extern "C" {
 /* flags for b200mrc_sauvola */
 #define B200MRC_SAUVOLA_OR_INTO      1 /* out |= fg   (mask_arr |= thres_arr, mrc.py:329)           */
 #define B200MRC_SAUVOLA_RAW_INVERTED 2 /* store !fg: exactly what binarise_sauvola writes (sauvola.pyx:153) */
+#define B200MRC_SAUVOLA_INVERT_INPUT 4 /* threshold 255 - p: the inverted line crop of create_hocr_mask (mrc.py:226, 235) */
 
 /* flags for b200mrc_decompose */
 #define B200MRC_DECOMPOSE_DENOISE_FAST 1 /* denoise_mask == 'fast' (mrc.py:384-390)                 */
@@ -150,6 +151,18 @@ B200MRC_API int    b200mrc_resample(const b200mrc_resample_plan *plan,
                         const uint8_t *in, int64_t in_pitch, int64_t in_page_stride,
                         uint8_t *out, int64_t out_pitch, int64_t out_page_stride, int n_pages,
                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* f1  create_hocr_mask (mrc.py:188-270): per text line, Sauvola (k = 0.1) on the crop and on the inverted crop
+ * (b200mrc_sauvola, B200MRC_SAUVOLA_INVERT_INPUT), np.count_nonzero of both (mrc.py:231, 236) and, for the
+ * undecided lines, mean_estimate_sigma of the two BOOLEAN results (mrc.py:253-254).  The two measurements run
+ * over a DEVICE array of crop descriptors, one CTA per crop:
+ *   ptr/pitch/width/height : a 0/1 byte plane (a Sauvola output);
+ *   keys                   : scratch of ((height+3)/2) * ((width+3)/2) uint64 (sigma only). */
+typedef struct {
+    const uint8_t *ptr; int64_t pitch; int32_t width, height; uint64_t *keys;
+} b200mrc_rect;
+B200MRC_API int b200mrc_rects_count_nonzero(const b200mrc_rect *rects_dev, int n_rects, uint32_t *counts_dev, void *stream);
+B200MRC_API int b200mrc_rects_sigma_bool(const b200mrc_rect *rects_dev, int n_rects, double *sigma_dev, void *stream);
 
 /* A12  special_gray_convert (grayconvert.py:38-66).  Two steps with a host decision between them,
  * exactly like the reference: (1) per-channel min / max / sum / sum-of-squares of each page

@@ -331,6 +331,58 @@ ORC_API double orc_estimate_sigma_crop(const uint8_t *gray, int W, int hs, int h
     return sigma;
 }
 
+
+/* mean_estimate_sigma on a BOOLEAN crop (mrc.py:253-254: estimate_sigma(thres)).  PyWavelets promotes a
+ * bool array to float64, so this is the same db2 'dd' band computed in double (True = 1.0) and a float64
+ * median.  img01: H x W bytes holding 0/1, row pitch `pitch`.  Third-party algorithm restated from its
+ * published form ("parity unpinned", like orc_estimate_sigma_crop). */
+static int cmp_double(const void *a, const void *b)
+{
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+ORC_API double orc_estimate_sigma_bool(const uint8_t *img01, int W, int H, int pitch)
+{
+    if (H <= 0 || W <= 0) return NAN;
+    int oh = (H + 3) / 2, ow = (W + 3) / 2;
+    double *d0 = (double *)malloc(sizeof(double) * (size_t)oh * W);
+    double *dd = (double *)malloc(sizeof(double) * (size_t)oh * ow);
+    if (!d0 || !dd) { free(d0); free(dd); return NAN; }
+    for (int o = 0; o < oh; o++)
+        for (int x = 0; x < W; x++) {
+            double sum = 0.0;
+            for (int j = 0; j < 4; j++) {
+                int yy = sym_idx(2 * o + 1 - j, H);
+                double p = img01[(size_t)yy * pitch + x] ? 1.0 : 0.0;
+                double prod = ORC_DB2_DEC_HI[j] * p;
+                sum = sum + prod;
+            }
+            d0[(size_t)o * W + x] = sum;
+        }
+    for (int y = 0; y < oh; y++)
+        for (int o = 0; o < ow; o++) {
+            double sum = 0.0;
+            for (int j = 0; j < 4; j++) {
+                double prod = ORC_DB2_DEC_HI[j] * d0[(size_t)y * W + sym_idx(2 * o + 1 - j, W)];
+                sum = sum + prod;
+            }
+            dd[(size_t)y * ow + o] = sum;
+        }
+    size_t cnt = 0, tot = (size_t)oh * ow;
+    for (size_t i = 0; i < tot; i++)
+        if (dd[i] != 0.0) dd[cnt++] = fabs(dd[i]);
+    double sigma;
+    if (cnt == 0) sigma = NAN;
+    else {
+        qsort(dd, cnt, sizeof(double), cmp_double);
+        double med = (cnt & 1) ? dd[cnt / 2] : (dd[cnt / 2 - 1] + dd[cnt / 2]) / 2.0;
+        sigma = med / 0.6744897501960817;
+    }
+    free(d0); free(dd);
+    return sigma;
+}
+
 ORC_API double orc_estimate_noise(const uint8_t *gray, int W, int H)
 {
     int hs, he, ws, we;

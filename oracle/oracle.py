@@ -49,6 +49,8 @@ def lib():
         L.orc_noise_crop.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, i32p]
         L.orc_estimate_sigma_crop.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_estimate_sigma_crop.restype = C.c_double
+        L.orc_estimate_sigma_bool.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_estimate_sigma_bool.restype = C.c_double
         L.orc_estimate_noise.argtypes = [u8p, C.c_int, C.c_int]
         L.orc_estimate_noise.restype = C.c_double
         L.orc_resample_ksize.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]
@@ -141,6 +143,12 @@ def estimate_sigma_full(gray):
     """estimate_sigma of a whole uint8 image held as float32 (no crop)."""
     gray = _u8(gray)
     return lib().orc_estimate_sigma_crop(_p(gray), gray.shape[1], 0, gray.shape[0], 0, gray.shape[1])
+
+
+def estimate_sigma_bool(arr):
+    """mean_estimate_sigma of a boolean array (mrc.py:253-254): float64 db2 'dd' median."""
+    a = np.ascontiguousarray(np.asarray(arr) != 0).view(np.uint8)
+    return lib().orc_estimate_sigma_bool(_p(a), a.shape[1], a.shape[0], a.shape[1])
 
 
 # --------------------------------------------------------------------------- thumbnail
@@ -246,13 +254,73 @@ def threshold_mask(gray, dpi=None, window=None, k=0.34, sigma_est=None):
     return sauvola(g, w, k=k), sigma_est
 
 
+def hocr_lines(hocr_word_data, image_width, image_height, downsample=None):
+    """The text-line boxes create_hocr_mask works on, in order (mrc.py:194-222)."""
+    out = []
+    for paragraph in hocr_word_data:
+        for line in paragraph['lines']:
+            coords = line['bbox']
+            line_text = ' '.join([word['text'] for word in line['words']])
+            line_confs = [word['confidence'] for word in line['words']]
+            line_conf = sum(line_confs) / len(line_confs) if len(line_confs) else 0
+            if line_text.strip() == '' or line_conf < 20:
+                continue
+            if downsample is not None:
+                coords = [int(x / downsample) for x in coords]
+            else:
+                coords = [int(x) for x in coords]
+            left, top, right, bottom = coords
+            if left == right or top == bottom:
+                continue
+            if (left >= right) or (top >= bottom):
+                continue
+            if (left < 0) or (right > image_width) or (top < 0) or (bottom > image_height):
+                continue
+            out.append((left, top, right, bottom))
+    return out
+
+
+def hocr_choice(ratio, inv_ratio, sigmas):
+    """mrc.py:238-263: 0 = leave the mask alone, 1 = thres, 2 = thres_invert.  `sigmas` is a callable returning
+    (ratio_sigma, inv_ratio_sigma); it is only called when the reference would call mean_estimate_sigma."""
+    if ratio < 0.3 or inv_ratio < 0.3:
+        if inv_ratio > 0.2 and ratio < 0.2:
+            return 1
+        ratio_sigma, inv_ratio_sigma = sigmas()
+        if inv_ratio < 0.3 and inv_ratio < ratio and \
+                (inv_ratio_sigma < ratio_sigma or (ratio_sigma < 0.1 and inv_ratio_sigma < 0.1)):
+            return 2
+        elif ratio < 0.2:
+            return 1
+    return 0
+
+
+def hocr_mask(gray, mask, hocr_word_data, downsample=None, dpi=None):
+    """create_hocr_mask (mrc.py:188-270) on a uint8 gray page; `mask` (bool) is modified in place."""
+    H, W = gray.shape
+    w = window_for_dpi(dpi)
+    for (left, top, right, bottom) in hocr_lines(hocr_word_data, W, H, downsample):
+        crop = np.ascontiguousarray(gray[top:bottom, left:right])
+        thres = sauvola(crop, w, k=0.1)
+        thres_inv = sauvola(255 - crop, w, k=0.1)
+        ratio = np.count_nonzero(thres) / crop.size
+        inv_ratio = np.count_nonzero(thres_inv) / crop.size
+        c = hocr_choice(ratio, inv_ratio, lambda: (estimate_sigma_bool(thres), estimate_sigma_bool(thres_inv)))
+        if c:
+            mask[top:bottom, left:right] = thres if c == 1 else thres_inv
+    return mask
+
+
 def decompose(image, dpi=None, bg_downsample=None, fg_downsample=None, denoise_mask=None,
-              window=None, sigma_est=None, mask_only=False):
-    """create_mrc_hocr_components (mrc.py:334-471) with hocr_word_data=[]; image: uint8 ndarray
-    H x W (mode L) or H x W x 3 (mode RGB).  Returns dict(mask, fg, bg, sigma, errors)."""
+              window=None, sigma_est=None, mask_only=False, hocr_word_data=(), downsample=None):
+    """create_mrc_hocr_components (mrc.py:334-471); image: uint8 ndarray H x W (mode L) or
+    H x W x 3 (mode RGB).  Returns dict(mask, fg, bg, sigma, errors)."""
     image = _u8(image)
     gray = image if image.ndim == 2 else rgb2gray(image)
     mask, sigma = threshold_mask(gray, dpi=dpi, window=window, sigma_est=sigma_est)
+    if hocr_word_data:
+        hm = hocr_mask(gray, np.zeros(gray.shape, bool), hocr_word_data, downsample=downsample, dpi=dpi)
+        mask = hm | mask                                                        # mrc.py:329
     if denoise_mask != DENOISE_NONE:
         if denoise_mask == DENOISE_FAST:
             mask = denoise(mask, 4, 2)

@@ -136,6 +136,8 @@ def load_reference_mrc(reference_dir='/root/reference'):
 
     def estimate_sigma(arr):
         a = np.asarray(arr)
+        if a.dtype == np.bool_:                              # create_hocr_mask (mrc.py:253-254)
+            return orc.estimate_sigma_bool(a)
         if a.dtype != np.float32 or np.any(a != np.floor(a)) or a.min() < 0 or a.max() > 255:
             raise NotImplementedError('stub estimate_sigma: only uint8-valued float32 input')
         return orc.estimate_sigma_full(np.ascontiguousarray(a).astype(np.uint8))

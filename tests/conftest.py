@@ -49,7 +49,28 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('hocr_'))
+
+
+def hocr_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and f.startswith('hocr_'))
+
+
+def load_hocr_golden(name, synth):
+    """Outputs of the imported reference create_mrc_hocr_components / create_hocr_mask with text-line boxes
+    (tests/golden/make_golden.py HOCR_CASES); page and hocr_word_data are regenerated from the seeds."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
+    idx, H, W, dpi, rgb, ds, bgd = (int(v) for v in z['params'])
+    dpi = None if dpi < 0 else dpi
+    ds = None if ds < 0 else ds
+    page = synth.make_page(idx, H, W, dpi=dpi or 100, rgb=bool(rgb), sigma_n=float(z['sigma_n']),
+                           invert_lines=tuple(int(v) for v in z['invert_lines']),
+                           noisy_dark_lines=tuple(int(v) for v in z['noisy_dark_lines']))
+    hocr = synth.page_hocr(H, W, dpi=dpi or 100, scale=float(ds or 1))
+    return dict(page=page, hocr=hocr, dpi=dpi, downsample=ds, bg_downsample=None if bgd < 0 else bgd, denoise=str(z['denoise']),
+                fg=z['fg'], bg=z['bg'], mask=np.unpackbits(z['mask'])[: H * W].reshape(H, W).astype(bool),
+                hocr_mask=np.unpackbits(z['hocr_mask'])[: H * W].reshape(H, W).astype(bool),
+                timing_keys=[str(k) for k in z['timing_keys']])
 
 
 def load_golden(name, synth):

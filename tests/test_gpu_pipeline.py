@@ -4,7 +4,7 @@ Bar (BASELINE.json): masks bit-exact; fg/bg within +-1 LSB (we assert exact equa
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden
+from conftest import golden_cases, load_golden, hocr_cases, load_hocr_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -197,3 +197,72 @@ def test_copy2d_roundtrip(eng):
     assert torch.equal(dst, src)
     assert bool((b.t[:, :, w * c:] == 9).all())                  # row padding untouched
     assert L.b200mrc_copy2d(None, 0, None, 0, 1, 1, 1, st) == _lib.ERR_INVALID
+
+
+@pytest.mark.parametrize('name', hocr_cases())
+def test_generator_with_hocr_lines_matches_golden_reference(eng, synth, orc, name):
+    """create_hocr_mask on the device (mrc.py:188-270): per-line Sauvola on crop / inverted crop, fill ratios, the
+    sigma tie-break and the pastes, then the usual path with mask |= thres."""
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    from archive_pdf_tools_b200 import mrc as pm, engine as E
+    g = load_hocr_golden(name, synth)
+    timing = []
+    gen = pkg.create_mrc_hocr_components(Image.fromarray(g['page']), g['hocr'], dpi=g['dpi'], downsample=g['downsample'],
+                                         bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'], timing_data=timing)
+    mask = next(gen); fg = next(gen); bg = next(gen)
+    assert np.array_equal(mask, g['mask']), int((mask != g['mask']).sum())
+    assert np.array_equal(fg, g['fg']) and np.array_equal(bg, g['bg'])
+    assert [k for k, _ in timing] == g['timing_keys']
+    # the hOCR mask on its own
+    gray = g['page'] if g['page'].ndim == 2 else orc.rgb2gray(g['page'])
+    gp = E.Plane(1, gray.shape[0], gray.shape[1], 1, eng.device).upload(gray[None])
+    mp = E.Plane(1, gray.shape[0], gray.shape[1], 1, eng.device)
+    mp.t.zero_()
+    pm.create_hocr_mask(gp, mp, g['hocr'], downsample=g['downsample'], dpi=g['dpi'])
+    assert np.array_equal(mp.numpy(np.bool_)[0], g['hocr_mask'])
+
+
+def test_rect_kernels_match_oracle(eng, orc):
+    """b200mrc_rects_count_nonzero / b200mrc_rects_sigma_bool against np.count_nonzero and the float64 restatement of
+    mean_estimate_sigma on boolean crops of assorted shapes (incl. 1-pixel-wide, all-false, all-true)."""
+    import ctypes as C
+    import torch
+    from archive_pdf_tools_b200 import _lib, engine as E
+    rng = np.random.default_rng(11)
+    shapes = [(1, 1), (1, 37), (40, 1), (2, 2), (3, 5), (10, 198), (17, 246), (33, 64), (21, 401)]
+    crops = []
+    for i, (h, w) in enumerate(shapes):
+        p = [0.05, 0.5, 0.9, 0.0, 1.0][i % 5]
+        a = (rng.random((h, w)) < p)
+        if i == 6:                                           # glyph-like structure instead of noise
+            a[:] = False; a[4:12, ::7] = True; a[8, :] = True
+        crops.append(a)
+    planes = [E.Plane(1, a.shape[0], a.shape[1], 1, eng.device).upload(a.view(np.uint8)[None]) for a in crops]
+    keys = [torch.empty(((a.shape[0] + 3) // 2) * ((a.shape[1] + 3) // 2), dtype=torch.int64, device=eng.device) for a in crops]
+    arr = (_lib.Rect * len(crops))()
+    for r, pl, k in zip(arr, planes, keys):
+        r.ptr, r.pitch, r.width, r.height, r.keys = pl.t.data_ptr(), pl.pitch, pl.w, pl.h, k.data_ptr()
+    rd = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(eng.device)
+    counts = torch.empty(len(crops), dtype=torch.int32, device=eng.device)
+    sig = torch.empty(len(crops), dtype=torch.float64, device=eng.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L = _lib.lib()
+    assert L.b200mrc_rects_count_nonzero(C.c_void_p(rd.data_ptr()), len(crops), C.c_void_p(counts.data_ptr()), st) == 0
+    assert L.b200mrc_rects_sigma_bool(C.c_void_p(rd.data_ptr()), len(crops), C.c_void_p(sig.data_ptr()), st) == 0
+    torch.cuda.synchronize()
+    assert counts.cpu().tolist() == [int(np.count_nonzero(a)) for a in crops]
+    for a, s in zip(crops, sig.cpu().tolist()):
+        exp = orc.estimate_sigma_bool(a)
+        assert (np.isnan(exp) and np.isnan(s)) or s == exp, (a.shape, s, exp)
+
+
+def test_sauvola_invert_input_flag(eng, orc):
+    from archive_pdf_tools_b200 import _lib, engine as E
+    rng = np.random.default_rng(3)
+    for (h, w, win) in ((10, 198, 25), (33, 70, 51), (5, 9, 25)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        src = E.Plane(1, h, w, 1, eng.device).upload(img[None])
+        dst = E.Plane(1, h, w, 1, eng.device)
+        eng.sauvola(src, dst, win, win, 0.1, 128.0, _lib.SAUVOLA_INVERT_INPUT)
+        assert np.array_equal(dst.numpy(np.bool_)[0], orc.sauvola(255 - img, win, k=0.1)), (h, w, win)

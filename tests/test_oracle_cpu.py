@@ -7,7 +7,7 @@
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden
+from conftest import golden_cases, load_golden, hocr_cases, load_hocr_golden
 
 SHAPES = [(1, 1), (3, 7), (10, 10), (40, 200), (200, 40), (77, 133), (129, 257)]
 
@@ -134,3 +134,53 @@ def test_invalid_denoise_option_raises(orc):
 def test_too_small_to_downsample(orc):
     res = orc.decompose(np.full((2, 9), 200, np.uint8), dpi=100, bg_downsample=3, denoise_mask='none', sigma_est=0.0)
     assert 'too-small-to-downsample' in res['errors'] and res['bg'].shape == (2, 9)
+
+
+@pytest.mark.parametrize('name', hocr_cases())
+def test_oracle_hocr_mask_vs_golden_reference(orc, synth, name):
+    """create_hocr_mask + the full generator with text-line boxes (mrc.py:188-270, 367-380): the restatement against
+    outputs of the imported reference.  mean_estimate_sigma of the boolean crops is the oracle restatement on both
+    sides (scikit-image is not installed): that one step stays "parity unpinned"."""
+    g = load_hocr_golden(name, synth)
+    page = g['page']
+    gray = page if page.ndim == 2 else orc.rgb2gray(page)
+    hm = orc.hocr_mask(gray, np.zeros(gray.shape, bool), g['hocr'], downsample=g['downsample'], dpi=g['dpi'])
+    assert np.array_equal(hm, g['hocr_mask'])
+    res = orc.decompose(page, dpi=g['dpi'], bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'],
+                        hocr_word_data=g['hocr'], downsample=g['downsample'])
+    assert np.array_equal(res['mask'], g['mask']) and np.array_equal(res['fg'], g['fg']) and np.array_equal(res['bg'], g['bg'])
+    plain = orc.decompose(page, dpi=g['dpi'], denoise_mask=g['denoise'], mask_only=True)
+    assert (plain['mask'] != g['mask']).any(), 'the fixture must exercise a line that changes the mask'
+
+
+def test_hocr_line_filter_and_choice_rule(orc, synth):
+    hocr = synth.page_hocr(330, 255, dpi=100)
+    lines = orc.hocr_lines(hocr, 255, 330)
+    total = sum(len(p['lines']) for p in hocr)
+    assert 0 < len(lines) < total - 4                      # low-confidence, empty-text, degenerate and outside boxes dropped
+    assert all(0 <= l < r <= 255 and 0 <= t < b <= 330 for (l, t, r, b) in lines)
+    assert orc.hocr_lines(hocr, 255, 330, downsample=2) != lines
+    # the polarity rule, branch by branch (mrc.py:238-263)
+    never = lambda: (_ for _ in ()).throw(AssertionError('sigma must not be evaluated'))
+    assert orc.hocr_choice(0.5, 0.5, never) == 0
+    assert orc.hocr_choice(0.1, 0.8, never) == 1
+    assert orc.hocr_choice(0.6, 0.25, lambda: (0.3, 0.2)) == 2
+    assert orc.hocr_choice(0.6, 0.25, lambda: (0.05, 0.06)) == 2
+    assert orc.hocr_choice(0.6, 0.25, lambda: (0.2, 0.3)) == 0
+    assert orc.hocr_choice(0.15, 0.1, lambda: (0.2, 0.3)) == 1
+    assert orc.hocr_choice(0.25, 0.1, lambda: (float('nan'), 0.3)) == 0
+
+
+def test_product_hocr_choice_matches_oracle(orc):
+    """Host logic of the product mirror (archive_pdf_tools_b200.mrc) against the restatement on a grid."""
+    from archive_pdf_tools_b200 import mrc as pm
+    vals = [0.0, 0.05, 0.1, 0.19, 0.2, 0.21, 0.29, 0.3, 0.31, 0.5, 0.9]
+    sig = [0.0, 0.05, 0.099, 0.1, 0.2, float('nan')]
+    for r in vals:
+        for ri in vals:
+            for s1 in sig:
+                for s2 in sig:
+                    exp = orc.hocr_choice(r, ri, lambda: (s1, s2))
+                    assert pm._hocr_choice(r, ri, (s1, s2)) == exp
+                    if not pm._needs_sigma(r, ri):
+                        assert pm._hocr_choice(r, ri, None) == exp
