@@ -15,7 +15,8 @@ from . import _lib
 from ._lib import B200MrcError, LIB_PATH
 from .engine import (MrcEngine, Plane, ThumbnailPlan, DecomposeBatch, window_for_dpi,
                      DENOISE_NONE, DENOISE_FAST, DENOISE_BREGMAN)
-from .mrc import threshold_image, create_mrc_hocr_components, decompose_pages, get_engine
+from .mrc import (threshold_image, create_mrc_hocr_components, create_hocr_mask, decompose_pages, downsample_image,
+                  packed_mask, get_engine)
 from .grayconvert import special_gray_convert
 
 __version__ = '0.1.0'

@@ -39,6 +39,36 @@ __global__ void __launch_bounds__(256) k_rects_count_nonzero(const b200mrc_rect 
     if (threadIdx.x == 0) counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
 }
 
+// f2  mask hand-off to the encoder (encode_mrc_mask, mrc.py:474-520: Image.fromarray(np_mask).save(png)): the
+// boolean mask as PIL mode-'1' rows, 8 pixels per byte, most significant bit first (== np.packbits(mask, axis=1)),
+// optionally inverted (recode.py:408: np_mask ^ True for --bw-pdf).  One thread per output byte.
+__global__ void __launch_bounds__(256) k_pack_mask(const uint8_t *mask, int64_t pitch, int64_t stride,
+                                                   uint8_t *out, int64_t opitch, int64_t ostride, int W, int H, int invert)
+{
+    const int bx = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, page = blockIdx.z;
+    const int nb = (W + 7) >> 3;
+    if (bx >= nb) return;
+    const uint8_t *row = mask + (int64_t)page * stride + (int64_t)y * pitch + 8 * bx;
+    uint32_t w0, w1;
+    if (8 * bx + 8 <= W && ((pitch | stride) & 3) == 0 && (((uintptr_t)mask) & 3) == 0) {
+        w0 = *reinterpret_cast<const uint32_t *>(row); w1 = *reinterpret_cast<const uint32_t *>(row + 4);
+    } else {
+        w0 = w1 = 0;
+        for (int j = 0; j < 8 && 8 * bx + j < W; j++) {
+            if (j < 4) w0 |= (uint32_t)row[j] << (8 * j); else w1 |= (uint32_t)row[j] << (8 * (j - 4));
+        }
+    }
+    // any non-zero byte = set; 4 bytes holding 0/1 -> one nibble, first pixel = highest bit
+    w0 = ((((w0 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w0) >> 7) & 0x01010101u;
+    w1 = ((((w1 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w1) >> 7) & 0x01010101u;
+    uint32_t b = (((w0 * 0x08040201u) >> 24) << 4) | ((w1 * 0x08040201u) >> 24);
+    if (invert) {
+        const int valid = min(8, W - 8 * bx);                // bits beyond the row stay 0, like np.packbits
+        b = (~b) & (0xffu << (8 - valid)) & 0xffu;
+    }
+    out[(int64_t)page * ostride + (int64_t)y * opitch + bx] = (uint8_t)b;
+}
+
 constexpr int SG_T = 1024;
 
 // 0-based rank `rank` among the non-zero keys of keys[0..n): 8 passes of 8 bits, most significant first
@@ -125,6 +155,20 @@ extern "C" int b200mrc_rects_count_nonzero(const b200mrc_rect *rects_dev, int n_
     if (n_rects < 0 || (n_rects && (!rects_dev || !counts_dev))) return B200MRC_ERR_INVALID;
     if (n_rects == 0) return B200MRC_OK;
     { ProfScope _ps("k_rects_count_nonzero", (cudaStream_t)stream); k_rects_count_nonzero<<<n_rects, 256, 0, (cudaStream_t)stream>>>(rects_dev, counts_dev); }
+    B200MRC_LAUNCH_CHECK();
+    return B200MRC_OK;
+}
+
+extern "C" int b200mrc_pack_mask(const uint8_t *mask, int64_t pitch, int64_t page_stride,
+                                 uint8_t *packed, int64_t packed_pitch, int64_t packed_page_stride,
+                                 int width, int height, int n_pages, int invert, void *stream)
+{
+    if (!mask || !packed || width <= 0 || height <= 0 || n_pages <= 0) return B200MRC_ERR_INVALID;
+    if (packed_pitch < (width + 7) / 8 || pitch < width) return B200MRC_ERR_INVALID;
+    if (height > 65535 || n_pages > 65535) return B200MRC_ERR_UNSUPPORTED;
+    dim3 grid(cdiv((width + 7) / 8, 256), height, n_pages);
+    { ProfScope _ps("k_pack_mask", (cudaStream_t)stream);
+      k_pack_mask<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, pitch, page_stride, packed, packed_pitch, packed_page_stride, width, height, invert ? 1 : 0); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

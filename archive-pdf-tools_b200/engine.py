@@ -191,6 +191,28 @@ class MrcEngine:
                                          f[0], f[1], f[2], n_fg, b[0], b[1], b[2], n_bg, img.w, img.h, img.n,
                                          wp, wb, _stream_ptr()), 'b200mrc_optimise')
 
+    def pack_mask(self, mask, invert=False):
+        """mask Plane -> uint8 device tensor [N, H, ceil(W/8)]: PIL mode-'1' rows (np.packbits(mask, axis=-1)), the
+        form encode_mrc_mask hands to the PNG/JBIG2 encoder (mrc.py:474-520); 8x fewer bytes to bring back."""
+        nb = (mask.w + 7) // 8
+        out = torch.empty((mask.n, mask.h, nb), dtype=torch.uint8, device=self.device)
+        L.check(L.lib().b200mrc_pack_mask(mask.ptr, mask.pitch, mask.page_stride, C.c_void_p(out.data_ptr()), nb, mask.h * nb,
+                                          mask.w, mask.h, mask.n, 1 if invert else 0, _stream_ptr()), 'b200mrc_pack_mask')
+        return out
+
+    def thumbnail_np(self, arr, req_w, req_h, reducing_gap=2.0, filter=BICUBIC):
+        """PIL Image.fromarray(arr).thumbnail((req_w, req_h), resample=filter, reducing_gap=...) on the device;
+        arr: uint8 [H,W] or [H,W,3].  Returns a new ndarray (arr itself when Pillow would not resize)."""
+        h, w = arr.shape[:2]
+        c = 1 if arr.ndim == 2 else arr.shape[2]
+        plan = ThumbnailPlan(w, h, c, req_w, req_h, reducing_gap, filter)
+        if plan.noop:
+            return arr
+        src = Plane(1, h, w, c, self.device).upload(arr[None], non_blocking=False)
+        dst = Plane(1, plan.out_h, plan.out_w, c, self.device)
+        self.resample(plan, src, dst)
+        return dst.numpy()[0]
+
     def resample(self, plan, src, dst):
         need = plan.workspace_bytes(src.n)
         wp, wb = self.workspace(need)

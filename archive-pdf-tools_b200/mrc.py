@@ -298,6 +298,29 @@ def create_mrc_hocr_components(image, hocr_word_data,
     return
 
 
+def downsample_image(image, downsample):
+    """The page pre-step of recode.py:368-372 -- image.thumbnail((w/downsample, h/downsample), resample=LANCZOS,
+    reducing_gap=None) -- on the device.  image: PIL 'L' / 'RGB'; returns a new PIL image (Pillow resizes in place)."""
+    from PIL import Image
+    if image.mode not in ('L', 'RGB'):
+        image = image.convert('RGB')
+    w, h = image.size
+    out = get_engine().thumbnail_np(np.asarray(image), w / downsample, h / downsample, reducing_gap=None, filter=E.LANCZOS)
+    return Image.fromarray(out)
+
+
+def packed_mask(mask_arr, invert=False):
+    """Boolean mask (H x W ndarray) -> (bytes of the PIL mode-'1' image, PIL image): what encode_mrc_mask
+    (mrc.py:474-520) builds with Image.fromarray(np_mask); `invert` is recode.py:408's np_mask ^ True."""
+    from PIL import Image
+    m = np.ascontiguousarray(mask_arr).view(np.uint8)
+    h, w = m.shape
+    eng = get_engine()
+    plane = E.Plane(1, h, w, 1, eng.device).upload(m[None], non_blocking=False)
+    data = eng.pack_mask(plane, invert=invert).cpu().numpy()[0].tobytes()
+    return data, Image.frombytes('1', (w, h), data)
+
+
 def decompose_pages(pages, dpi=None, window=None, bg_downsample=None, fg_downsample=None,
                     denoise_mask=DENOISE_FAST, mask_only=False, sigma=None, batch=None):
     """Batched form of create_mrc_hocr_components for N equally-shaped pages held in HOST memory

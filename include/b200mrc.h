@@ -164,6 +164,13 @@ typedef struct {
 B200MRC_API int b200mrc_rects_count_nonzero(const b200mrc_rect *rects_dev, int n_rects, uint32_t *counts_dev, void *stream);
 B200MRC_API int b200mrc_rects_sigma_bool(const b200mrc_rect *rects_dev, int n_rects, double *sigma_dev, void *stream);
 
+/* f2  The mask as the encoder wants it (encode_mrc_mask, mrc.py:474-520 saves Image.fromarray(np_mask), a PIL
+ * mode-'1' image): rows of ceil(width/8) bytes, 8 pixels per byte, first pixel in the most significant bit
+ * (== np.packbits(mask, axis=1)); `invert` applies recode.py:408's np_mask ^ True on the way. */
+B200MRC_API int b200mrc_pack_mask(const uint8_t *mask, int64_t pitch, int64_t page_stride,
+                      uint8_t *packed, int64_t packed_pitch, int64_t packed_page_stride,
+                      int width, int height, int n_pages, int invert, void *stream);
+
 /* A12  special_gray_convert (grayconvert.py:38-66).  Two steps with a host decision between them,
  * exactly like the reference: (1) per-channel min / max / sum / sum-of-squares of each page
  * (`stats_out`: n_pages x 3 x 4 uint64 on the DEVICE: min, max, sum, sumsq), (2) per-pixel level

@@ -266,3 +266,40 @@ def test_sauvola_invert_input_flag(eng, orc):
         dst = E.Plane(1, h, w, 1, eng.device)
         eng.sauvola(src, dst, win, win, 0.1, 128.0, _lib.SAUVOLA_INVERT_INPUT)
         assert np.array_equal(dst.numpy(np.bool_)[0], orc.sauvola(255 - img, win, k=0.1)), (h, w, win)
+
+
+def test_packed_mask_matches_packbits_and_pil(eng):
+    """b200mrc_pack_mask: the PIL mode-'1' rows encode_mrc_mask builds (mrc.py:490: Image.fromarray(np_mask))."""
+    from PIL import Image
+    import torch
+    import archive_pdf_tools_b200 as pkg
+    from archive_pdf_tools_b200 import engine as E
+    rng = np.random.default_rng(17)
+    for (h, w) in ((1, 1), (3, 7), (5, 8), (9, 17), (40, 255), (33, 256), (21, 2550)):
+        m = rng.random((h, w)) < 0.3
+        for inv in (False, True):
+            data, im = pkg.packed_mask(m, invert=inv)
+            ref = m ^ inv
+            assert data == np.packbits(ref, axis=1).tobytes(), (h, w, inv)
+            assert im.mode == '1' and np.array_equal(np.array(im), np.array(Image.fromarray(ref)))
+    # batched planes, arbitrary non-zero bytes count as set
+    m = (rng.integers(0, 4, (3, 30, 100)) * 85).astype(np.uint8)
+    pl = E.Plane(3, 30, 100, 1, eng.device).upload(m)
+    out = eng.pack_mask(pl).cpu().numpy()
+    assert np.array_equal(out, np.packbits(m != 0, axis=2))
+
+
+def test_lanczos_pre_downsample_matches_pillow(eng, orc):
+    """recode.py:368-372: image.thumbnail((w/ds, h/ds), resample=LANCZOS, reducing_gap=None)."""
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    rng = np.random.default_rng(23)
+    for (h, w, c, ds) in ((120, 90, 3, 2), (201, 333, 1, 3), (97, 64, 3, 1.5), (64, 64, 1, 4), (50, 40, 3, 1)):
+        arr = rng.integers(0, 256, (h, w, 3) if c == 3 else (h, w), dtype=np.uint8)
+        im = Image.fromarray(arr)
+        ref = im.copy()
+        ref.thumbnail((w / ds, h / ds), resample=Image.LANCZOS, reducing_gap=None)
+        out = pkg.downsample_image(im, ds)
+        assert out.size == ref.size and out.mode == ref.mode
+        assert np.array_equal(np.array(out), np.array(ref)), (h, w, c, ds)
+        assert np.array_equal(orc.thumbnail(arr, w / ds, h / ds, reducing_gap=None, filter=orc.LANCZOS), np.array(ref))

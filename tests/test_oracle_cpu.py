@@ -184,3 +184,14 @@ def test_product_hocr_choice_matches_oracle(orc):
                     assert pm._hocr_choice(r, ri, (s1, s2)) == exp
                     if not pm._needs_sigma(r, ri):
                         assert pm._hocr_choice(r, ri, None) == exp
+
+
+def test_oracle_lanczos_thumbnail_vs_pillow(orc):
+    """The page pre-downsample of recode.py:368-372 (LANCZOS, reducing_gap=None) against the installed Pillow."""
+    from PIL import Image
+    rng = np.random.default_rng(29)
+    for (h, w, c, ds) in ((120, 90, 3, 2), (201, 333, 1, 3), (97, 64, 3, 1.5), (64, 64, 1, 4)):
+        arr = rng.integers(0, 256, (h, w, 3) if c == 3 else (h, w), dtype=np.uint8)
+        ref = Image.fromarray(arr)
+        ref.thumbnail((w / ds, h / ds), resample=Image.LANCZOS, reducing_gap=None)
+        assert np.array_equal(orc.thumbnail(arr, w / ds, h / ds, reducing_gap=None, filter=orc.LANCZOS), np.array(ref)), (h, w, c, ds)
