@@ -20,6 +20,7 @@
 //     FP64 with __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
 // Algorithmic HBM bytes: 1 B/px read + 1 B/px written.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200mrc {
 
@@ -274,7 +275,7 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     const int sw_max = (SE - p.ext_left - p.r) / 4 * 4;          // >= 768
     p.n_strips = cdiv(width, sw_max);
     p.strip_w = (cdiv(width, p.n_strips) + 3) / 4 * 4;
-    p.band_h = 128;
+    { const char *e = getenv("B200MRC_SAUVOLA_BAND"); p.band_h = e ? atoi(e) : 128; if (p.band_h < 16) p.band_h = 16; }
     p.n_bands = cdiv(height, p.band_h);
     p.km1 = k - 1.0;
     p.k2 = k * k / R / R;                                         // sauvola.pyx:60
