@@ -303,3 +303,28 @@ def test_lanczos_pre_downsample_matches_pillow(eng, orc):
         assert out.size == ref.size and out.mode == ref.mode
         assert np.array_equal(np.array(out), np.array(ref)), (h, w, c, ds)
         assert np.array_equal(orc.thumbnail(arr, w / ds, h / ds, reducing_gap=None, filter=orc.LANCZOS), np.array(ref))
+
+
+def test_config4_600dpi_page_both_windows(eng, synth, orc):
+    """BASELINE config 4: 600-DPI scan 6600x5100 RGB, denoise fast, bg/3 -- Sauvola window 51 as the config names it
+    (explicit window) and the API-derived 151 for dpi=600."""
+    import archive_pdf_tools_b200 as pkg
+    page = synth.make_page(40, 6600, 5100, dpi=600)
+    for kw in (dict(window=51), dict(dpi=600)):
+        res = pkg.decompose_pages(page[None], bg_downsample=3, denoise_mask='fast', **kw)
+        exp = orc.decompose(page, bg_downsample=3, denoise_mask='fast', **kw)
+        assert res['sigma'][0] == exp['sigma']
+        assert np.array_equal(res['mask'][0], exp['mask']), int((res['mask'][0] != exp['mask']).sum())
+        assert np.array_equal(res['fg'][0], exp['fg']) and np.array_equal(res['bg'][0], exp['bg'])
+        assert res['bg'][0].shape == (2200, 1700, 3)
+
+
+def test_config5_mask_only_200dpi_gray_batch(eng, synth, orc):
+    """BASELINE config 5: gray pages 2200x1700 @200 DPI (window 51), mask-only (first yield), denoise fast."""
+    import archive_pdf_tools_b200 as pkg
+    pages = np.stack([synth.make_page(50 + i, 2200, 1700, dpi=200, rgb=False, halftone=(i == 2)) for i in range(3)])
+    res = pkg.decompose_pages(pages, dpi=200, denoise_mask='fast', mask_only=True)
+    assert 'fg' not in res and 'bg' not in res
+    for i in range(3):
+        exp = orc.decompose(pages[i], dpi=200, denoise_mask='fast', mask_only=True)
+        assert np.array_equal(res['mask'][i], exp['mask']), i
