@@ -24,6 +24,7 @@
 // (k_opt_fir fmt 1) so that numerator assembly is one multiply-add per word.
 #include "common.cuh"
 #include "tma.cuh"
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -52,9 +53,10 @@ struct IirWParams {
 
 template <int C> struct WarpSmem {
     static constexpr int ROWB = SWW * C;                    // bytes of one strip row (384 / 128)
+    static constexpr int RGBS = 512;                        // stage bytes for the pixels: [ROWB] (TMA) or [32 lanes][16] (cp.async)
     static constexpr int off_mbar = 0;                      // IST x 8
-    static constexpr int off_rgb = 64;                      // [IST][ROWB]
-    static constexpr int off_rec = off_rgb + IST * ROWB;    // [IST][SWW * 8]
+    static constexpr int off_rgb = 64;                      // [IST][RGBS]
+    static constexpr int off_rec = off_rgb + IST * RGBS;    // [IST][SWW * 8]  (TMA: row order; cp.async: [2][32 lanes][16])
     static constexpr int off_ost = off_rec + IST * SWW * 8; // [3][2][ROWB]
     static constexpr int off_rbg = off_ost + 6 * ROWB;      // bg ring, packed px  [NBG][SWW] u32
     static constexpr int off_rfg = off_rbg + NBG * SWW * 4; // fg ring, lanes form [NFG][2][SWW] u32
@@ -76,6 +78,17 @@ __device__ __forceinline__ void st_relaxed4(uint32_t *p, uint32_t a, uint32_t b,
 {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ bool tags_ok(const uint4 v, uint32_t tag)
 {
     return ((((v.x ^ tag) | (v.y ^ tag)) | ((v.z ^ tag) | (v.w ^ tag))) & TAGMASK) == 0;
@@ -91,7 +104,10 @@ __device__ __forceinline__ void div3(const uint32_t *Mtab, uint32_t nr2, uint32_
     q_g = __umulhi(ng2, m31);
 }
 
-template <int C>
+// ASYNC = false: inputs by TMA bulk loads + mbarriers, outputs by bulk stores (lane 0 drives them);
+// ASYNC = true : inputs by lane-private cp.async copies (no barrier, no proxy fence), outputs re-tiled through smem and
+//                stored as 16-byte words by the first lanes -- fewer instructions on the per-row path.
+template <int C, bool ASYNC>
 __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
 {
     using SM = WarpSmem<C>;
@@ -140,11 +156,39 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
 
     auto issue_row = [&](int row, int s) {                   // lane 0
         mbar_expect_tx(&mbar[s], bytesRGB + bytesRec);
-        tma_load(rgbS + s * ROWB, img + (int64_t)row * p.ipitch, bytesRGB, &mbar[s]);
+        tma_load(rgbS + s * SM::RGBS, img + (int64_t)row * p.ipitch, bytesRGB, &mbar[s]);
         tma_load(recS + s * (SWW * 8), rec + (int64_t)row * p.rpitch, bytesRec, &mbar[s]);
     };
-    if (lane == 0)
+    // cp.async mode: every lane copies the 4 records + 4 pixels of its own columns into its own 16-byte slots
+    const int col0 = x0 + lane * K;
+    const bool inside = col0 < W;
+    const bool acopy = inside && (int64_t)(col0 + K) * C <= p.ipitch && (int64_t)(col0 + K) * 8 <= p.rpitch;
+    const uint8_t *a_img = img + (int64_t)lane * K * C, *a_rec = rec + (int64_t)lane * K * 8;    // next row to copy
+    int a_st = 0;
+    auto issue_async = [&](int row) {                        // one commit group per call, stages in row order
+        if (row < H) {
+            uint8_t *dr = recS + a_st * (SWW * 8) + lane * 16, *dg = rgbS + a_st * SM::RGBS + lane * 16;
+            if (acopy) {
+                cp_async16(dr, a_rec); cp_async16(dr + 512, a_rec + 16);
+                if (C == 3) { cp_async4(dg, a_img); cp_async4(dg + 4, a_img + 4); cp_async4(dg + 8, a_img + 8); }
+                else cp_async4(dg, a_img);
+            } else if (inside) {                             // ragged last group that would leave the row pitch: guarded loads
+                for (int k = 0; k < K; k++) {
+                    const bool v = col0 + k < W;
+                    reinterpret_cast<uint2 *>(k < 2 ? dr : dr + 512)[k & 1] = v ? *reinterpret_cast<const uint2 *>(a_rec + 8 * k) : make_uint2(0, 0);
+                    for (int c = 0; c < C; c++) dg[k * C + c] = v ? a_img[k * C + c] : 0;
+                }
+            }
+            a_img += p.ipitch; a_rec += p.rpitch;
+            if (++a_st == IST) a_st = 0;
+        }
+        cp_async_commit();
+    };
+    if (ASYNC) {
+        for (int r = 0; r < IST - 1; r++) issue_async(r);
+    } else if (lane == 0) {
         for (int r = 0; r < IST && r < H; r++) issue_row(r, r);
+    }
     // mailbox rows of the left neighbour are prefetched two rows ahead (lanes 0-7, 16 B each)
     const bool hl = has_left && lane < 8;
     uint4 pfA = make_uint4(0, 0, 0, 0), pfB = make_uint4(0, 0, 0, 0);      // rows y+1 / y+2
@@ -155,27 +199,33 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
 #pragma unroll
     for (int k = 0; k < K; k++) Cf_rb[k] = Cf_g[k] = Cb_rb[k] = Cb_g[k] = 0;
     int slot = 0, par = 0, ob = 0, rf = 0, rbg = 0, hs = 0;
+    uint8_t *o_fg = ofg, *o_bg = obg;                        // output rows (cp.async mode)
 
     for (int y = 0; y < H; y++) {
         if (hl && y + 2 < H) pfB = ld_relaxed4(mb_in + (int64_t)(y + 2) * MBW + lane * 4);
-        if (lane == 0) tma_wait_read<2>();                   // output staging buffer `ob` is free again
-        __syncwarp();
-        mbar_wait(&mbar[slot], (uint32_t)par);               // this row's RGB + records have landed
+        if (ASYNC) {
+            issue_async(y + IST - 1);                        // into the stage consumed in row y-1
+            cp_async_wait<IST - 1>();                        // this lane's copies of row y have landed
+        } else {
+            if (lane == 0) tma_wait_read<2>();               // output staging buffer `ob` is free again
+            __syncwarp();
+            mbar_wait(&mbar[slot], (uint32_t)par);           // this row's RGB + records have landed
+        }
 
         // ---- inputs of the lane's 4 pixels
         uint32_t lo[K], hi[K], px[K], img_rb[K], img_g[K];
         {
-            const uint32_t *rp = reinterpret_cast<const uint32_t *>(recS + slot * (SWW * 8)) + lane * 8;
-            const uint4 a = ld4(rp), b = ld4(rp + 4);
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(recS + slot * (SWW * 8)) + (ASYNC ? lane * 4 : lane * 8);
+            const uint4 a = ld4(rp), b = ld4(rp + (ASYNC ? 128 : 4));
             lo[0] = a.x; hi[0] = a.y; lo[1] = a.z; hi[1] = a.w; lo[2] = b.x; hi[2] = b.y; lo[3] = b.z; hi[3] = b.w;
         }
         uint32_t raw[3];
         if (C == 3) {
-            const uint32_t *gp = reinterpret_cast<const uint32_t *>(rgbS + slot * ROWB) + lane * 3;
+            const uint32_t *gp = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS) + (ASYNC ? lane * 4 : lane * 3);
             raw[0] = gp[0]; raw[1] = gp[1]; raw[2] = gp[2];
             px[0] = raw[0]; px[1] = perm(raw[0], raw[1], 0x5543); px[2] = perm(raw[1], raw[2], 0x4432); px[3] = raw[2] >> 8;
         } else {
-            raw[0] = reinterpret_cast<const uint32_t *>(rgbS + slot * ROWB)[lane]; raw[1] = raw[2] = 0;
+            raw[0] = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS)[ASYNC ? lane * 4 : lane]; raw[1] = raw[2] = 0;
             px[0] = perm(raw[0], 0, 0x4000); px[1] = perm(raw[0], 0, 0x4111); px[2] = perm(raw[0], 0, 0x4222); px[3] = perm(raw[0], 0, 0x4333);
         }
 #pragma unroll
@@ -297,7 +347,7 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
                 reinterpret_cast<uint32_t *>(sf)[lane] = perm(perm(pf_[0], pf_[1], 0x0040), perm(pf_[2], pf_[3], 0x0040), 0x5410);
                 reinterpret_cast<uint32_t *>(sb)[lane] = need_bg ? perm(perm(pbg[0], pbg[1], 0x0040), perm(pbg[2], pbg[3], 0x0040), 0x5410) : raw[0];
             }
-            fence_proxy_async();
+            if (!ASYNC) fence_proxy_async();
         }
 
         // ---- hand the new column sums (those of row y+1) to the right neighbour
@@ -323,7 +373,16 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
             pfA = pfB;
         }
         __syncwarp();
-        if (lane == 0) {
+        if (ASYNC) {
+            // the staged rows leave as 16-byte words (row bytes rounded up to 16, like the bulk stores)
+            if (lane * 16 < (int)bytesRGB) {
+                const uint4 vf = *reinterpret_cast<const uint4 *>(ost + (ob * 2 + 0) * ROWB + lane * 16);
+                const uint4 vb = *reinterpret_cast<const uint4 *>(ost + (ob * 2 + 1) * ROWB + lane * 16);
+                *reinterpret_cast<uint4 *>(o_fg + lane * 16) = vf;
+                *reinterpret_cast<uint4 *>(o_bg + lane * 16) = vb;
+            }
+            o_fg += p.fpitch; o_bg += p.bpitch;
+        } else if (lane == 0) {
             tma_store(ofg + (int64_t)y * p.fpitch, ost + (ob * 2 + 0) * ROWB, bytesRGB);
             tma_store(obg + (int64_t)y * p.bpitch, ost + (ob * 2 + 1) * ROWB, bytesRGB);
             tma_commit();
@@ -335,7 +394,7 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
         if (++rbg == NBG) rbg = 0;
         hs ^= 1;
     }
-    if (lane == 0) tma_wait_all<0>();
+    if (!ASYNC && lane == 0) tma_wait_all<0>();
 }
 
 }  // namespace
@@ -384,7 +443,9 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     const size_t smem = iirw_smem_bytes(C, wpc);
     if (smem > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
     B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
-    const void *kern = C == 3 ? (const void *)k_opt_iir_w<3> : (const void *)k_opt_iir_w<1>;
+    const bool use_tma = getenv("B200MRC_IIRW_TMA") != nullptr;        // A/B switch: TMA-fed form of the same sweep
+    const void *kern = use_tma ? (C == 3 ? (const void *)k_opt_iir_w<3, false> : (const void *)k_opt_iir_w<1, false>)
+                               : (C == 3 ? (const void *)k_opt_iir_w<3, true> : (const void *)k_opt_iir_w<1, true>);
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&p};
     { ProfScope _ps("k_opt_iir_w", st); B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3((unsigned)cdiv(jobs, wpc)), dim3(32 * wpc), args, smem, st)); }
