@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "tma.cuh"
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -443,7 +444,10 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     const size_t smem = iirw_smem_bytes(C, wpc);
     if (smem > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
     B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
-    const bool use_tma = getenv("B200MRC_IIRW_TMA") != nullptr;        // A/B switch: TMA-fed form of the same sweep
+    // Feed: TMA bulk copies when the batch fills the machine (>= 4 warp strips per SM: equal or slightly faster there),
+    // lane-private cp.async copies for small batches (shorter row latency).  B200MRC_IIRW_FEED=tma|async overrides.
+    const char *feed = getenv("B200MRC_IIRW_FEED");
+    const bool use_tma = feed ? !strcmp(feed, "tma") : jobs >= 4 * dev_info().sm_count;
     const void *kern = use_tma ? (C == 3 ? (const void *)k_opt_iir_w<3, false> : (const void *)k_opt_iir_w<1, false>)
                                : (C == 3 ? (const void *)k_opt_iir_w<3, true> : (const void *)k_opt_iir_w<1, true>);
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

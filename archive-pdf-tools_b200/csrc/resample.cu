@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         const int b = (px * F + t) * C + c;
-                        acc[px][c] += (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu) * p.kh[t];
+                        acc[px][c] += (int)__byte_perm(w[b >> 2], 0, 0x4440 | (b & 3)) * p.kh[t];   // one PRMT per byte
                     }
             uint32_t ow_[C];                                  // 4*C output bytes = C words
 #pragma unroll
@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
             for (int t = 0; t < T; t++) {
                 const uint32_t w = *reinterpret_cast<const uint32_t *>(q + t * HROW);
                 const int kv = p.kv[t];
-                a0 += (int)(w & 0xffu) * kv; a1 += (int)((w >> 8) & 0xffu) * kv; a2 += (int)((w >> 16) & 0xffu) * kv; a3 += (int)(w >> 24) * kv;
+                a0 += (int)__byte_perm(w, 0, 0x4440) * kv; a1 += (int)__byte_perm(w, 0, 0x4441) * kv;
+                a2 += (int)__byte_perm(w, 0, 0x4442) * kv; a3 += (int)(w >> 24) * kv;
             }
         } else {
             const int yy = oy0 + oy, cnt = p.bounds_v[2 * yy + 1];
