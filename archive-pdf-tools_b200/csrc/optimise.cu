@@ -32,7 +32,7 @@
 #include <cstdlib>
 
 namespace b200mrc {
-size_t iirg_mailbox_bytes(int W, int H, int N);       // optimise_ghost.cu
+size_t iirw_mailbox_words(int W, int H, int N);        // optimise_warp.cu
 size_t optimise_split_rec_bytes(int W, int H, int N);  // optimise_split.cu
 namespace {
 
@@ -288,7 +288,7 @@ OptLayout opt_layout(int W, int H, int N)
     const size_t Smax = (size_t)cdiv(W, 32);
     Carver c;
     OptLayout L;
-    L.off_mailbox = c.take<uint32_t>(std::max((size_t)N * Smax * H * 2 * OH, iirg_mailbox_bytes(W, H, N) / sizeof(uint32_t)));
+    L.off_mailbox = c.take<uint32_t>(std::max((size_t)N * Smax * H * 2 * OH, iirw_mailbox_words(W, H, N)));
     L.off_prog = c.take<int>((size_t)N * Smax);
     L.off_ticket = c.take<unsigned>(4);
     L.off_rec = c.take<uint8_t>(optimise_split_rec_bytes(W, H, N));   // FIR record plane (optimise_split.cu)
@@ -298,17 +298,11 @@ OptLayout opt_layout(int W, int H, int N)
 
 }  // namespace
 
-int launch_optimise_fast(const uint8_t *mask, int64_t mpitch, int64_t mstride,
-                         const uint8_t *img, int64_t ipitch, int64_t istride, int C,
-                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
-                         uint8_t *obg, int64_t bpitch, int64_t bstride,
-                         int W, int H, int N, uint32_t *mailbox, int *prog, unsigned *ticket, cudaStream_t st);
-
 int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                           const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                           uint8_t *ofg, int64_t fpitch, int64_t fstride,
                           uint8_t *obg, int64_t bpitch, int64_t bstride,
-                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, int *prog, unsigned *ticket, cudaStream_t st);
+                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, unsigned *ticket, cudaStream_t st);
 
 size_t optimise_workspace_bytes(int W, int H, int N) { return opt_layout(W, H, N).total; }
 
@@ -321,19 +315,12 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     const OptLayout L = opt_layout(W, H, N);
     if (!workspace || workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
     uint8_t *ws = (uint8_t *)workspace;
-    const char *path = getenv("B200MRC_OPT_PATH");          // "split" (default) | "fused" | "generic": A/B switch for profiling
+    const char *path = getenv("B200MRC_OPT_PATH");          // "split" (default) | "generic": A/B switch for profiling
     if (nfg == 3 && nbg == 10 && (!path || !strcmp(path, "split"))) {
-        // production path: parallel FIR record plane + short sequential IIR sweep (optimise_split.cu)
+        // production path: parallel FIR record plane + row-sequential warp-strip sweep (optimise_split.cu)
         const int frc = launch_optimise_split(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
                                               obg, bpitch, bstride, W, H, N, ws + L.off_rec, (uint32_t *)(ws + L.off_mailbox),
-                                              (int *)(ws + L.off_prog), (unsigned *)(ws + L.off_ticket), st);
-        if (frc != B200MRC_ERR_UNSUPPORTED) return frc;
-    }
-    if (nfg == 3 && nbg == 10 && (!path || strcmp(path, "generic"))) {
-        // single fused sweep (TMA-fed, specialised for the reference's n); falls through when it does not apply
-        const int frc = launch_optimise_fast(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
-                                             obg, bpitch, bstride, W, H, N, (uint32_t *)(ws + L.off_mailbox),
-                                             (int *)(ws + L.off_prog), (unsigned *)(ws + L.off_ticket), st);
+                                              (unsigned *)(ws + L.off_ticket), st);
         if (frc != B200MRC_ERR_UNSUPPORTED) return frc;
     }
     OptPlan plan;
