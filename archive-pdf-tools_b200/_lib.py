@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libb200mrc.so')
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_ALIGNMENT = 0, -1, -2, -3, -4
 SAUVOLA_OR_INTO, SAUVOLA_RAW_INVERTED, SAUVOLA_INVERT_INPUT = 1, 2, 4
-DECOMPOSE_DENOISE_FAST, DECOMPOSE_MASK_ONLY, DECOMPOSE_NO_NOISE_EST = 1, 2, 4
+DECOMPOSE_DENOISE_FAST, DECOMPOSE_MASK_ONLY, DECOMPOSE_NO_NOISE_EST, DECOMPOSE_OR_INTO_MASK = 1, 2, 4, 8
 MAX_WINDOW, MAX_OPT_N = 255, 16
 COPY_H2D, COPY_D2H, COPY_D2D = 1, 2, 3
 

@@ -222,9 +222,10 @@ extern "C" int b200mrc_decompose(const b200mrc_decompose_args *a, void *stream)
     rc = launch_gray_blur(a->img, a->img_pitch, a->img_page_stride, C, gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page,
                           W, H, N, sigma_used, nullptr, st);
     if (rc) return rc;
-    // ---- Sauvola: mask = threshold_image(gray)   (the hOCR mask is empty: OR is a plain store)
+    // ---- Sauvola: mask = threshold_image(gray), or mask |= ... when the caller filled in the hOCR line masks
     rc = b200mrc_sauvola(gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page, a->mask, a->mask_pitch, a->mask_page_stride,
-                         W, H, N, a->window, a->window, a->k, a->R, 0, st);
+                         W, H, N, a->window, a->window, a->k, a->R,
+                         (a->flags & B200MRC_DECOMPOSE_OR_INTO_MASK) ? B200MRC_SAUVOLA_OR_INTO : 0, st);
     if (rc) return rc;
     // ---- denoise
     if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) {

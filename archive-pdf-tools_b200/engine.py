@@ -91,6 +91,20 @@ class Plane:
         return a.reshape(shape).view(dtype)
 
 
+class PageView:
+    """One page of a Plane batch as a Plane-like object (n = 1, same memory)."""
+
+    def __init__(self, plane, i):
+        self.n, self.h, self.w, self.c, self.pitch = 1, plane.h, plane.w, plane.c, plane.pitch
+        self.t = plane.t[i:i + 1]
+
+    ptr = Plane.ptr
+    page_stride = Plane.page_stride
+    view = Plane.view
+    numpy = Plane.numpy
+    download = Plane.download
+
+
 class ThumbnailPlan:
     """PIL Image.thumbnail((int(w/f), int(h/f))) plan (mrc.py:420-434 / 454-468)."""
 
@@ -259,13 +273,13 @@ class DecomposeBatch:
         self._args = None
         self._ws = None
 
-    def _build_args(self, window, k, R, denoise_fast, use_sigma_in):
+    def _build_args(self, window, k, R, denoise_fast, use_sigma_in, or_into=False):
         a = L.DecomposeArgs()
         a.img, a.img_pitch, a.img_page_stride, a.channels = self.img.ptr, self.img.pitch, self.img.page_stride, self.c
         a.width, a.height, a.n_pages = self.w, self.h, self.n
         a.window, a.k, a.R = window, k, R
         a.flags = (L.DECOMPOSE_DENOISE_FAST if denoise_fast else 0) | (L.DECOMPOSE_MASK_ONLY if self.mask_only else 0) | \
-                  (L.DECOMPOSE_NO_NOISE_EST if use_sigma_in else 0)
+                  (L.DECOMPOSE_NO_NOISE_EST if use_sigma_in else 0) | (L.DECOMPOSE_OR_INTO_MASK if or_into else 0)
         a.sigma_in = C.c_void_p(self.sigma_in.data_ptr()) if use_sigma_in else None
         a.sigma_out = C.c_void_p(self.sigma.data_ptr())
         a.mask, a.mask_pitch, a.mask_page_stride = self.mask.ptr, self.mask.pitch, self.mask.page_stride
@@ -282,18 +296,19 @@ class DecomposeBatch:
         a.workspace, a.workspace_bytes = C.c_void_p(self._ws.data_ptr()), self._ws.numel()
         return a
 
-    def run(self, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST, sigma=None):
+    def run(self, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST, sigma=None, or_into_mask=False):
         """Enqueue the whole pipeline (b200mrc_decompose) on the current stream.  `sigma`: optional
-        per-page injected sigma_est (host sequence) replacing the on-device estimate."""
+        per-page injected sigma_est (host sequence) replacing the on-device estimate.  or_into_mask: self.mask
+        already holds the hOCR line masks (mrc.create_hocr_mask) and the page threshold is OR-ed in."""
         if denoise_mask not in (DENOISE_NONE, DENOISE_FAST):
             if denoise_mask == DENOISE_BREGMAN:
                 raise NotImplementedError('denoise_bregman is out of scope (SURVEY.md section 2)')
             raise ValueError('Invalid denoise option:', denoise_mask)              # mrc.py:396
         if sigma is not None:
             self.sigma_in.copy_(torch.as_tensor(np.asarray(sigma, np.float64)))
-        key = (window, k, R, denoise_mask == DENOISE_FAST, sigma is not None)
+        key = (window, k, R, denoise_mask == DENOISE_FAST, sigma is not None, bool(or_into_mask))
         if self._args is None or self._args[0] != key:
-            self._args = (key, self._build_args(window, k, R, denoise_mask == DENOISE_FAST, sigma is not None))
+            self._args = (key, self._build_args(window, k, R, denoise_mask == DENOISE_FAST, sigma is not None, bool(or_into_mask)))
         L.check(L.lib().b200mrc_decompose(C.byref(self._args[1]), _stream_ptr()), 'b200mrc_decompose')
         return self
 

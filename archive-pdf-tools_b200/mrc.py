@@ -322,11 +322,14 @@ def packed_mask(mask_arr, invert=False):
 
 
 def decompose_pages(pages, dpi=None, window=None, bg_downsample=None, fg_downsample=None,
-                    denoise_mask=DENOISE_FAST, mask_only=False, sigma=None, batch=None):
+                    denoise_mask=DENOISE_FAST, mask_only=False, sigma=None, batch=None,
+                    hocr_word_data=None, downsample=None):
     """Batched form of create_mrc_hocr_components for N equally-shaped pages held in HOST memory
     (uint8 ndarray [N,H,W] or [N,H,W,3], or a pinned CPU tensor): one H2D copy, one
     b200mrc_decompose, D2H of the results.  Returns dict(mask, fg, bg, sigma, errors).
-    `batch`: a DecomposeBatch to reuse (device buffers + workspace)."""
+    `batch`: a DecomposeBatch to reuse (device buffers + workspace).  `hocr_word_data`: optional list with one
+    hocr_word_data structure per page (empty / None entries for pages without text boxes); those pages get their
+    hOCR line masks (create_hocr_mask) before the page threshold is OR-ed in."""
     eng = get_engine()
     shape = tuple(pages.shape)
     n, h, w = shape[:3]
@@ -334,7 +337,20 @@ def decompose_pages(pages, dpi=None, window=None, bg_downsample=None, fg_downsam
     if batch is None:
         batch = eng.make_batch(n, h, w, c, bg_downsample, fg_downsample, mask_only)
     batch.img.upload(pages)
-    batch.run(window if window is not None else E.window_for_dpi(dpi), denoise_mask=denoise_mask, sigma=sigma)
+    or_into = False
+    if hocr_word_data is not None and any(hocr_word_data):
+        assert len(hocr_word_data) == n
+        batch.mask.t.zero_()
+        or_into = True
+        gray = E.Plane(1, h, w, 1, eng.device) if c != 1 else None
+        for i, hd in enumerate(hocr_word_data):
+            if not hd:
+                continue
+            page_img = E.PageView(batch.img, i)
+            if c != 1:
+                eng.gray_blur(page_img, gray, None)          # the plain 'L' page (mrc.py:358-363)
+            create_hocr_mask(gray if c != 1 else page_img, E.PageView(batch.mask, i), hd, downsample=downsample, dpi=dpi)
+    batch.run(window if window is not None else E.window_for_dpi(dpi), denoise_mask=denoise_mask, sigma=sigma, or_into_mask=or_into)
     res = dict(mask=batch.mask.numpy(np.bool_), sigma=batch.sigma.cpu().numpy(), errors=set(batch.errors))
     if not mask_only:
         res['fg'] = batch.fg.numpy()

@@ -59,6 +59,7 @@ extern "C" {
 #define B200MRC_DECOMPOSE_DENOISE_FAST 1 /* denoise_mask == 'fast' (mrc.py:384-390)                 */
 #define B200MRC_DECOMPOSE_MASK_ONLY    2 /* stop after the first yield (recode.py:398-407, --bw-pdf) */
 #define B200MRC_DECOMPOSE_NO_NOISE_EST 4 /* skip estimate_noise; use sigma_in (or 0 => no blur)     */
+#define B200MRC_DECOMPOSE_OR_INTO_MASK 8 /* `mask` already holds the hOCR line masks: mask |= thres (mrc.py:329) */
 
 B200MRC_API int         b200mrc_version(void);
 B200MRC_API const char *b200mrc_error_string(int status);

@@ -328,3 +328,18 @@ def test_config5_mask_only_200dpi_gray_batch(eng, synth, orc):
     for i in range(3):
         exp = orc.decompose(pages[i], dpi=200, denoise_mask='fast', mask_only=True)
         assert np.array_equal(res['mask'][i], exp['mask']), i
+
+
+def test_batched_decompose_with_hocr_matches_oracle(eng, synth, orc):
+    """decompose_pages with per-page text boxes: pages with and without hOCR data in one batch."""
+    import archive_pdf_tools_b200 as pkg
+    H, W, dpi = 330, 255, 100
+    pages = np.stack([synth.make_page(60 + i, H, W, dpi=dpi, sigma_n=1.0, invert_lines=(2,), noisy_dark_lines=(5, 7)) for i in range(3)])
+    hocr = [synth.page_hocr(H, W, dpi=dpi), [], synth.page_hocr(H, W, dpi=dpi, low_conf_every=3)]
+    res = pkg.decompose_pages(pages, dpi=dpi, bg_downsample=3, denoise_mask='fast', hocr_word_data=hocr)
+    for i in range(3):
+        exp = orc.decompose(pages[i], dpi=dpi, bg_downsample=3, denoise_mask='fast', hocr_word_data=hocr[i])
+        assert np.array_equal(res['mask'][i], exp['mask']), (i, int((res['mask'][i] != exp['mask']).sum()))
+        assert np.array_equal(res['fg'][i], exp['fg']) and np.array_equal(res['bg'][i], exp['bg']), i
+    plain = pkg.decompose_pages(pages, dpi=dpi, bg_downsample=3, denoise_mask='fast')
+    assert not np.array_equal(plain['mask'][0], res['mask'][0]) and np.array_equal(plain['mask'][1], res['mask'][1])
