@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_resample_v(const ResampleParams p)
 // the same T coefficients, which sit in the kernel's constant bank; a thread of the horizontal pass loads the
 // (3F+T)*C input bytes of 4 adjacent outputs as aligned words once and extracts every byte once.  Tiles that
 // touch the image border (clipped, renormalised windows) take the table-driven form of the same arithmetic.
-constexpr int TOW = 32, TOH = 16;
+constexpr int TOW = 32, TOH = 32;
 
 struct TileParams {
     const uint8_t *in; int64_t in_pitch, in_stride;

@@ -50,6 +50,7 @@ __device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx
     return w;
 }
 
+template <bool KNEG>
 __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
 {
     // prefix of column sums for the current row, SoA layout, double buffered
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
                     const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
                     const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
                     const double lhs = __dmul_rn(t, t);
-                    const bool fg = p.kneg ? ((t <= 0.0) && (lhs >= rhs)) : ((t <= 0.0) || (lhs <= rhs));
+                    const bool fg = KNEG ? ((t <= 0.0) && (lhs >= rhs)) : ((t <= 0.0) || (lhs <= rhs));
                     bits |= (fg ? 1u : 0u) << (8 * j);
                 }
             } else {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
                         const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
                         const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
                         const double lhs = __dmul_rn(t, t);
-                        if (p.kneg) fg = (t <= 0.0) && (lhs >= rhs);
+                        if (KNEG) fg = (t <= 0.0) && (lhs >= rhs);
                         else        fg = (t <= 0.0) || (lhs <= rhs);
                     }
                     bits |= fg << (8 * j);
@@ -283,7 +284,9 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     p.flags = flags;
 
     dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_pages);
-    { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream); k_sauvola_mask<<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
+    { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream);
+      if (p.kneg) k_sauvola_mask<true><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else k_sauvola_mask<false><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }
