@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_resample_v(const ResampleParams p)
 // the same T coefficients, which sit in the kernel's constant bank; a thread of the horizontal pass loads the
 // (3F+T)*C input bytes of 4 adjacent outputs as aligned words once and extracts every byte once.  Tiles that
 // touch the image border (clipped, renormalised windows) take the table-driven form of the same arithmetic.
-constexpr int TOW = 32, TOH = 32;
+constexpr int TOW = 32;                 // tile width; the tile height is a template parameter (32 in production)
 
 struct TileParams {
     const uint8_t *in; int64_t in_pitch, in_stride;
@@ -183,7 +183,7 @@ struct TileParams {
     int kh[16], kv[16];
 };
 
-template <int C, int F, int T>
+template <int C, int F, int T, int TOH>
 __global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
 {
     constexpr int RMAX = F * TOH + T, HROW = TOW * C;
@@ -419,7 +419,7 @@ extern "C" b200mrc_resample_plan *b200mrc_thumbnail_plan_create(int width, int h
         find_uniform(bh, kh, pl->ksize_h, OW, Fh, Th, pl->offx, pl->ux0, pl->ux1, pl->kh);
         find_uniform(bv, kv, pl->ksize_v, OH, Fv, Tv, pl->offy, pl->uy0, pl->uy1, pl->kv);
         const bool ok = pl->fx == 1 && pl->fy == 1 && pl->need_h && pl->need_v && Fh == Fv && Th == Tv && Fh == 3 && Th == 12 &&
-                        ((pl->offx * channels) & 3) == 0 && pl->ux1 - pl->ux0 >= TOW && pl->uy1 - pl->uy0 >= TOH;
+                        ((pl->offx * channels) & 3) == 0 && pl->ux1 - pl->ux0 >= TOW && pl->uy1 - pl->uy0 >= 16;
         pl->tile_F = ok ? Fh : 0; pl->tile_T = ok ? Th : 0;
     }
     int rc = upload(bh, &pl->d_bounds_h);
@@ -490,17 +490,26 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         return B200MRC_OK;
     }
     if (pl->tile_F == 3 && pl->tile_T == 12 && !(src_pitch & 3) && !(src_stride & 3) && !((uintptr_t)src & 3) &&
-        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, TOH) <= 65535 && !getenv("B200MRC_RESAMPLE_2PASS")) {
+        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, 16) <= 65535 && !getenv("B200MRC_RESAMPLE_2PASS")) {
         TileParams t;
         t.in = src; t.in_pitch = src_pitch; t.in_stride = src_stride; t.out = out; t.out_pitch = out_pitch; t.out_stride = out_page_stride;
         t.in_w = pl->SW; t.in_h = pl->SH; t.out_w = pl->OW; t.out_h = pl->OH; t.ksize_h = pl->ksize_h; t.ksize_v = pl->ksize_v;
         t.bounds_h = pl->d_bounds_h; t.kk_h = pl->d_kk_h; t.bounds_v = pl->d_bounds_v; t.kk_v = pl->d_kk_v;
         t.offx = pl->offx; t.offy = pl->offy; t.ux0 = pl->ux0; t.ux1 = pl->ux1; t.uy0 = pl->uy0; t.uy1 = pl->uy1;
         memcpy(t.kh, pl->kh, sizeof(t.kh)); memcpy(t.kv, pl->kv, sizeof(t.kv));
-        dim3 grid(cdiv(pl->OW, TOW), cdiv(pl->OH, TOH), n_pages);
+        const char *the = getenv("B200MRC_TILE_H");
+        const int toh = the ? atoi(the) : 32;
+        dim3 grid(cdiv(pl->OW, TOW), cdiv(pl->OH, toh == 64 ? 64 : (toh == 16 ? 16 : 32)), n_pages);
         { ProfScope _ps("k_resample_tile", st);
-          if (pl->C == 1) k_resample_tile<1, 3, 12><<<grid, 256, 0, st>>>(t);
-          else k_resample_tile<3, 3, 12><<<grid, 256, 0, st>>>(t); }
+          if (pl->C == 1) {
+              if (toh == 64) k_resample_tile<1, 3, 12, 64><<<grid, 256, 0, st>>>(t);
+              else if (toh == 16) k_resample_tile<1, 3, 12, 16><<<grid, 256, 0, st>>>(t);
+              else k_resample_tile<1, 3, 12, 32><<<grid, 256, 0, st>>>(t);
+          } else {
+              if (toh == 64) k_resample_tile<3, 3, 12, 64><<<grid, 256, 0, st>>>(t);
+              else if (toh == 16) k_resample_tile<3, 3, 12, 16><<<grid, 256, 0, st>>>(t);
+              else k_resample_tile<3, 3, 12, 32><<<grid, 256, 0, st>>>(t);
+          } }
         B200MRC_LAUNCH_CHECK();
         return B200MRC_OK;
     }
