@@ -50,8 +50,8 @@ __device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx
     return w;
 }
 
-template <bool KNEG>
-__global__ void __launch_bounds__(ST, 4) k_sauvola_mask(const SauvolaParams p)
+template <bool KNEG, int MINB>
+__global__ void __launch_bounds__(ST, MINB) k_sauvola_mask(const SauvolaParams p)
 {
     // prefix of column sums for the current row, SoA layout, double buffered
     __shared__ uint2 sP[2][SK * (ST + 1)];
@@ -285,8 +285,13 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
 
     dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_pages);
     { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream);
-      if (p.kneg) k_sauvola_mask<true><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else k_sauvola_mask<false><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
+      const char *mb = getenv("B200MRC_SAUVOLA_MINB");
+      const int minb = mb ? atoi(mb) : 4;
+      if (p.kneg) k_sauvola_mask<true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else if (minb == 5) k_sauvola_mask<false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else if (minb == 6) k_sauvola_mask<false, 6><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else if (minb == 3) k_sauvola_mask<false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else k_sauvola_mask<false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }
