@@ -109,25 +109,43 @@ __global__ void __launch_bounds__(DT) k_mask_denoise(const DenoiseParams p)
     const int64_t words_page = (int64_t)p.H * p.Ww;
     const int64_t total_words = words_page * p.N;
 
-    // ---------------- phase 0: pack bytes -> bits
-    for (int64_t g = (int64_t)blockIdx.x * DT + tid; g < total_words; g += (int64_t)nblocks * DT) {
-        const int page = (int)(g / words_page);
-        const int64_t rem = g - (int64_t)page * words_page;
-        const int y = (int)(rem / p.Ww), j = (int)(rem - (int64_t)y * p.Ww);
+    // ---------------- phase 0: pack bytes -> bits (one thread per 32-pixel word; 32-bit index arithmetic when it fits)
+    auto pack_word = [&](int page, int y, int j, int64_t g) {
         const uint8_t *row = p.mask + (int64_t)page * p.stride + (int64_t)y * p.pitch + 32 * j;
         const int valid = min(32, p.W - 32 * j);
         uint32_t word = 0;
+        if (valid == 32 && (((uintptr_t)row) & 15) == 0) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (4 * k < valid) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(row + 4 * k);
-                const uint32_t nib = (((w & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
-                word |= nib << (4 * k);
+            for (int k = 0; k < 8; k++) word |= ((((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (4 * k < valid) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t *>(row + 4 * k);
+                    const uint32_t nib = (((w & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+                    word |= nib << (4 * k);
+                }
             }
+            if (valid < 32) word &= (1u << valid) - 1u;
         }
-        if (valid < 32) word &= (1u << valid) - 1u;
         p.Mb[g] = word;
         p.Rb[g] = word;
+    };
+    if (total_words < 0x7fffffffll) {
+        const uint32_t wp = (uint32_t)words_page, ww = (uint32_t)p.Ww, tw = (uint32_t)total_words;
+        for (uint32_t g = blockIdx.x * DT + tid; g < tw; g += nblocks * DT) {
+            const uint32_t page = g / wp, rem = g - page * wp, y = rem / ww;
+            pack_word((int)page, (int)y, (int)(rem - y * ww), (int64_t)g);
+        }
+    } else {
+        for (int64_t g = (int64_t)blockIdx.x * DT + tid; g < total_words; g += (int64_t)nblocks * DT) {
+            const int page = (int)(g / words_page);
+            const int64_t rem = g - (int64_t)page * words_page;
+            const int y = (int)(rem / p.Ww);
+            pack_word(page, y, (int)(rem - (int64_t)y * p.Ww), g);
+        }
     }
     grid_barrier(p.bar, nblocks);
 
