@@ -2,26 +2,28 @@
 // (n_fg = 3 / n_bg = 10; internetarchivepdf/mrc.py:412-415, 439-449; semantics
 // cython/optimiser.pyx:153-429) as free-running WARP strips.
 //
-//   out[y,x] = (FIR(y,x) + IIR(y,x)) / den(y,x)      FIR, den: record plane written by k_opt_fir
+//   out[y,x] = (FIR(y,x) + IIR(y,x)) / den(y,x)      FIR, den: record plane written by k_opt_fir_w
 //   IIR      = sum of `out` over the n x n box above-left (n = 3 for fg pixels, 10 for bg pixels)
 //
 // One warp owns a strip of 128 columns (4 adjacent columns per lane) of one page and marches down
 // its rows.  Nothing in the row loop is CTA-wide:
 //   * window sums come from the left lanes by warp shuffles; only lane 0 needs the neighbouring
-//     strip, whose column sums arrive through a global mailbox row (128 B) prefetched one row ahead;
+//     strip, whose column sums arrive through a global mailbox row (128 B) prefetched two rows ahead;
 //   * strips of a page are pipelined: a strip runs a couple of rows behind its left neighbour.  The
 //     hand-off needs no fence and no progress counter: every mailbox word carries an 8-bit launch
 //     epoch in the spare bits of its two 16-bit lanes (sums are < 4096), so a word is either stale
 //     (tag mismatch -> poll again) or complete; jobs are ticketed in dependency order, so any
 //     residency is deadlock-free;
-//   * every warp feeds itself: its lane 0 issues the TMA bulk loads of its input rows (RGB + 8-byte
-//     records, IST rows ahead, one mbarrier per stage) and the bulk stores of its staged fg/bg rows;
+//   * every warp feeds itself.  Large batches: its lane 0 issues the TMA bulk loads of its input rows (RGB +
+//     8-byte records, IST rows ahead, one mbarrier per stage) and the bulk stores of its staged fg/bg rows.
+//     Small batches (the machine is not full, row latency is everything): lane-private cp.async copies and
+//     re-tiled 16-byte stores, no barrier and no proxy fence (template parameter ASYNC);
 //   * column sums live in registers in 16-bit lanes (r | b << 16, g); the last n output rows are
 //     smem rings private to each lane (no synchronisation); rows without a mask pixel in the strip
 //     (the common case) take a short path: fg = quotient, bg = copy of the input row.
 // The truncating division is one multiply-high: floor(num/den) = umulhi(2*num, ceil(2^31/den)),
 // exact for num <= 255*den, den <= 500; records of fg pixels arrive pre-doubled in 16-bit lanes
-// (k_opt_fir fmt 1) so that numerator assembly is one multiply-add per word.
+// (optimise_firw.cu) so that numerator assembly is one multiply-add per word.
 #include "common.cuh"
 #include "tma.cuh"
 #include <cstdlib>
