@@ -52,6 +52,7 @@ struct IirWParams {
     uint32_t *mailbox;                  // [N][S][H][MBW]
     unsigned *ticket;
     uint32_t tag;                       // epoch spread over TAGMASK
+    unsigned psleep;                    // trio form: producer back-off (ns) when no stage is free
 };
 
 template <int C> struct WarpSmem {
@@ -400,9 +401,405 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
     if (!ASYNC && lane == 0) tma_wait_all<0>();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_opt_iir_w3: the same sweep with a strip served by THREE warps of one CTA.  The fg recurrence (n = 3) and the bg
+// recurrence (n = 10) never read each other's outputs, so each gets its own warp and its row step is about half as
+// long as the combined one (the sweep is bound by the length of that dependent chain, not by bytes); a third warp only
+// feeds them.  The two compute warps share the input stages (RGB + records cross HBM once) and nothing else:
+//   * producer warp: per row waits for empty[s] (two arrivals: both compute warps are done with the stage), arms
+//     full[s] with the byte count and issues the two TMA bulk loads; runs up to NST rows ahead;
+//   * fg / bg warp: waits for full[s], computes its layer, stages its output row in smem and stores it as 16-byte
+//     words (no bulk store: no proxy fence, no single-lane section on the row path), then lane 0 arrives on empty[s];
+//     each owns its ring, its mailbox words (fg: 24-31, bg: 0-23), its half of the halo, and polls only its own words
+//     of the left neighbour's mailbox row (same fence-free tagged hand-off as above).
+template <int C, int NST> struct TrioSmem {
+    static constexpr int ROWB = SWW * C;
+    static constexpr int RGBS = 512;
+    static constexpr int off_full = 0;                      // NST x 8
+    static constexpr int off_empty = NST * 8;               // NST x 8
+    static constexpr int off_job = NST * 16;                // int
+    static constexpr int off_rgb = (NST * 16 + 4 + 127) / 128 * 128;   // [NST][RGBS]
+    static constexpr int off_rec = off_rgb + NST * RGBS;    // [NST][SWW * 8]
+    static constexpr int off_ost = off_rec + NST * SWW * 8; // [2 buffers][2 layers][ROWB]
+    static constexpr int off_rbg = off_ost + 4 * ROWB;      // bg ring, packed px  [NBG][SWW] u32
+    static constexpr int off_rfg = off_rbg + NBG * SWW * 4; // fg ring, lanes form [NFG][2][SWW] u32
+    static constexpr int off_halo = off_rfg + NFG * 2 * SWW * 4;   // [2][MBW] u32
+    static constexpr int bytes = (off_halo + 2 * MBW * 4 + 127) / 128 * 128;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// TPC strips per CTA: warps 2t / 2t+1 are the fg / bg warps of strip t, the last warp feeds all of them.
+template <int C, int NST, int TPC>
+__global__ void __launch_bounds__(32 * (2 * TPC + 1), TPC == 2 ? 5 : 1) k_opt_iir_w3(const IirWParams p)
+{
+    using SM = TrioSmem<C, NST>;
+    constexpr int ROWB = SM::ROWB;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int wid = (int)__reduce_max_sync(FULL, threadIdx.x >> 5);      // warp-uniform for the compiler
+    const bool is_prod = wid == 2 * TPC;
+    const int role = is_prod ? 0 : 1 + (wid & 1);                        // 0: producer, 1: fg warp, 2: bg warp
+    uint32_t *Mtab = reinterpret_cast<uint32_t *>(smem);
+    uint8_t *wb = smem + MTAB_BYTES + (size_t)(is_prod ? 0 : wid >> 1) * SM::bytes;
+
+    for (int d = 1 + (int)threadIdx.x; d <= MAXDEN; d += blockDim.x) Mtab[d] = (uint32_t)((0x80000000ull + d - 1) / (unsigned long long)d);
+    if (threadIdx.x == 0) Mtab[0] = 0;
+    {
+        const int n16 = TPC * SM::bytes / 16;
+        uint4 *z = reinterpret_cast<uint4 *>(smem + MTAB_BYTES);
+        for (int i = (int)threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    uint64_t *full = reinterpret_cast<uint64_t *>(wb + SM::off_full), *empty = reinterpret_cast<uint64_t *>(wb + SM::off_empty);
+    volatile int *jobslot = reinterpret_cast<volatile int *>(wb + SM::off_job);
+    uint8_t *rgbS = wb + SM::off_rgb, *recS = wb + SM::off_rec, *ost = wb + SM::off_ost;
+    uint32_t *ringB = reinterpret_cast<uint32_t *>(wb + SM::off_rbg);
+    uint32_t *ringF = reinterpret_cast<uint32_t *>(wb + SM::off_rfg);
+    uint32_t *halo = reinterpret_cast<uint32_t *>(wb + SM::off_halo);
+
+    if (is_prod && lane == 0) {
+#pragma unroll
+        for (int t = 0; t < TPC; t++) {                      // consecutive tickets: neighbouring strips share the CTA
+            uint8_t *wt = smem + MTAB_BYTES + (size_t)t * SM::bytes;
+            *reinterpret_cast<volatile int *>(wt + SM::off_job) = (int)atomicAdd(p.ticket, 1u);
+            for (int s = 0; s < NST; s++) {
+                mbar_init(reinterpret_cast<uint64_t *>(wt + SM::off_full) + s, 1);
+                mbar_init(reinterpret_cast<uint64_t *>(wt + SM::off_empty) + s, 2);
+            }
+        }
+        fence_mbar_init();
+    }
+    fence_proxy_async();                                     // the zero fill precedes the bulk copies into the same smem
+    __syncthreads();                                         // tickets + barrier init visible to every warp; last CTA-wide barrier
+
+    if (is_prod) {
+        // =========================================== producer: one thread feeds the CTA's strips ===========================================
+        if (lane != 0) return;
+        const uint8_t *gi[TPC], *gr[TPC];
+        uint32_t nb_rgb[TPC], nb_rec[TPC];
+        int yy[TPC], sl[TPC], pr[TPC];
+#pragma unroll
+        for (int t = 0; t < TPC; t++) {
+            const int jb = *reinterpret_cast<volatile int *>(smem + MTAB_BYTES + (size_t)t * SM::bytes + SM::off_job);
+            const bool valid = jb < p.N * p.S;
+            const int pg = valid ? jb / p.S : 0, stp = valid ? jb - pg * p.S : 0;
+            const int oc = min(p.W - stp * SWW, SWW);
+            nb_rgb[t] = (uint32_t)((oc * C + 15) & ~15); nb_rec[t] = (uint32_t)((oc * 8 + 15) & ~15);
+            gi[t] = p.img + (int64_t)pg * p.istride + (int64_t)stp * SWW * C;
+            gr[t] = p.rec + (int64_t)pg * p.rstride + (int64_t)stp * SWW * 8;
+            yy[t] = valid ? 0 : p.H; sl[t] = 0; pr[t] = 0;
+        }
+        for (;;) {
+            bool any = false, prog = false;
+#pragma unroll
+            for (int t = 0; t < TPC; t++) {
+                if (yy[t] < p.H) {
+                    any = true;
+                    uint8_t *wt = smem + MTAB_BYTES + (size_t)t * SM::bytes;
+                    uint64_t *fl = reinterpret_cast<uint64_t *>(wt + SM::off_full) + sl[t];
+                    // a stage is refilled once both compute warps have released the row it held
+                    if (yy[t] < NST || mbar_test(reinterpret_cast<uint64_t *>(wt + SM::off_empty) + sl[t], (uint32_t)(pr[t] ^ 1))) {
+                        mbar_expect_tx(fl, nb_rgb[t] + nb_rec[t]);
+                        tma_load(wt + SM::off_rgb + sl[t] * SM::RGBS, gi[t], nb_rgb[t], fl);
+                        tma_load(wt + SM::off_rec + sl[t] * (SWW * 8), gr[t], nb_rec[t], fl);
+                        gi[t] += p.ipitch; gr[t] += p.rpitch;
+                        yy[t]++;
+                        if (++sl[t] == NST) { sl[t] = 0; pr[t] ^= 1; }
+                        prog = true;
+                    }
+                }
+            }
+            if (!any) break;
+            if (!prog) __nanosleep(p.psleep);
+        }
+        return;
+    }
+    const int job = (int)__reduce_max_sync(FULL, (unsigned)*jobslot);
+    if (job >= p.N * p.S) return;
+    const int page = job / p.S, strip = job - page * p.S;
+    const int W = p.W, H = p.H;
+    const int x0 = strip * SWW;
+    const int ocols = min(W - x0, SWW);
+    const uint32_t bytesRGB = (uint32_t)((ocols * C + 15) & ~15);
+    const bool has_left = strip > 0, has_right = strip + 1 < p.S;
+    const uint32_t tag = p.tag;
+    int slot = 0, par = 0;
+
+    // mailbox rows: mine (row y+1 is written while row y is processed) and the left neighbour's
+    uint32_t *mb_o = p.mailbox + ((int64_t)page * p.S + strip) * (int64_t)H * MBW + MBW;
+    const uint32_t *mb_i = (has_left ? p.mailbox + ((int64_t)page * p.S + strip - 1) * (int64_t)H * MBW : p.mailbox) + MBW;
+    int ob = 0, hs = 0;
+
+    if (role == 1) {
+        // =========================================== fg warp ===========================================
+        uint8_t *o_fg = p.ofg + (int64_t)page * p.fstride + (int64_t)x0 * C + lane * 16;
+        const bool hl = has_left && lane < 2;                // words 24..31 of the neighbour's mailbox row
+        mb_i += 24 + lane * 4;                               // row y+1 of the neighbour (this lane's words)
+        uint4 pfA = make_uint4(0, 0, 0, 0), pfB = make_uint4(0, 0, 0, 0);      // rows y+1 / y+2
+        if (hl && 1 < H) pfA = ld_relaxed4(mb_i);
+        uint32_t Cf_rb[K], Cf_g[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) Cf_rb[k] = Cf_g[k] = 0;
+        int rf = 0;
+
+        for (int y = 0; y < H; y++) {
+            if (hl && y + 2 < H) pfB = ld_relaxed4(mb_i + MBW);
+            mbar_wait(&full[slot], (uint32_t)par);           // this row's RGB + records have landed
+
+            uint32_t lo[K], hi[K];
+            {
+                const uint32_t *rp = reinterpret_cast<const uint32_t *>(recS + slot * (SWW * 8)) + lane * 8;
+                const uint4 a = ld4(rp), b = ld4(rp + 4);
+                lo[0] = a.x; hi[0] = a.y; lo[1] = a.z; hi[1] = a.w; lo[2] = b.x; hi[2] = b.y; lo[3] = b.z; hi[3] = b.w;
+            }
+            const bool any_m = __any_sync(FULL, (int)(hi[0] | hi[1] | hi[2] | hi[3]) < 0);
+
+            // ---- fg windows: sums of Cf over the 3 columns to the left
+            uint32_t sf_rb[K], sf_g[K];
+            {
+                uint32_t l1r = __shfl_up_sync(FULL, Cf_rb[3], 1), l2r = __shfl_up_sync(FULL, Cf_rb[2], 1), l3r = __shfl_up_sync(FULL, Cf_rb[1], 1);
+                uint32_t l1g = __shfl_up_sync(FULL, Cf_g[3], 1), l2g = __shfl_up_sync(FULL, Cf_g[2], 1), l3g = __shfl_up_sync(FULL, Cf_g[1], 1);
+                if (lane == 0) {
+                    const uint4 hr = ld4(halo + hs * MBW + 24), hg = ld4(halo + hs * MBW + 28);
+                    l3r = hr.y; l2r = hr.z; l1r = hr.w; l3g = hg.y; l2g = hg.z; l1g = hg.w;
+                }
+                const uint32_t ar = l2r + l1r, br = Cf_rb[0] + Cf_rb[1], ag = l2g + l1g, bgs = Cf_g[0] + Cf_g[1];
+                sf_rb[0] = ar + l3r; sf_rb[1] = ar + Cf_rb[0]; sf_rb[2] = br + l1r; sf_rb[3] = br + Cf_rb[2];
+                sf_g[0] = ag + l3g;  sf_g[1] = ag + Cf_g[0];   sf_g[2] = bgs + l1g; sf_g[3] = bgs + Cf_g[2];
+            }
+
+            // ---- quotients (records of mask pixels are of the other type: their quotient is discarded below; the
+            //      divisor comes straight from the record -- 2 * numerator < 2^16 never carries into its lane)
+            uint32_t of_rb[K], of_g[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t t_rb = sf_rb[k] * 2u + lo[k], t_gd = sf_g[k] * 2u + hi[k];
+                div3(Mtab, t_rb & 0xffffu, t_gd & 0xffffu, t_rb >> 16, hi[k] >> 16, of_rb[k], of_g[k]);
+            }
+            if (any_m) {
+                // mask pixels keep the image
+                uint32_t px[K];
+                if (C == 3) {
+                    const uint32_t *gp = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS) + lane * 3;
+                    const uint32_t r0 = gp[0], r1 = gp[1], r2 = gp[2];
+                    px[0] = r0; px[1] = perm(r0, r1, 0x5543); px[2] = perm(r1, r2, 0x4432); px[3] = r2 >> 8;
+                } else {
+                    const uint32_t r0 = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS)[lane];
+                    px[0] = perm(r0, 0, 0x4000); px[1] = perm(r0, 0, 0x4111); px[2] = perm(r0, 0, 0x4222); px[3] = perm(r0, 0, 0x4333);
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const bool m = (int)hi[k] < 0;
+                    of_rb[k] = m ? perm(px[k], 0, 0x4240) : of_rb[k];
+                    of_g[k] = m ? perm(px[k], 0, 0x4441) : of_g[k];
+                }
+            }
+
+            // ---- column sums: + out[y], - out[y-3] (lane-private ring; zero-initialised = rows above the page)
+            {
+                uint32_t o_rb[K], o_g[K];
+                un4(ld4(ringF + (rf * 2 + 0) * SWW + lane * 4), o_rb);
+                un4(ld4(ringF + (rf * 2 + 1) * SWW + lane * 4), o_g);
+#pragma unroll
+                for (int k = 0; k < K; k++) { Cf_rb[k] += of_rb[k] - o_rb[k]; Cf_g[k] += of_g[k] - o_g[k]; }
+                st4(ringF + (rf * 2 + 0) * SWW + lane * 4, of_rb);
+                st4(ringF + (rf * 2 + 1) * SWW + lane * 4, of_g);
+            }
+            // ---- hand the new column sums (those of row y+1) to the right neighbour
+            if (has_right && y + 1 < H && lane == 31) {
+                st_relaxed4(mb_o + 24, Cf_rb[0] | tag, Cf_rb[1] | tag, Cf_rb[2] | tag, Cf_rb[3] | tag);
+                st_relaxed4(mb_o + 28, Cf_g[0] | tag, Cf_g[1] | tag, Cf_g[2] | tag, Cf_g[3] | tag);
+            }
+            mb_o += MBW;
+
+            // ---- stage the output row
+            uint8_t *sf = ost + (ob * 2 + 0) * ROWB;
+            {
+                uint32_t pf_[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) pf_[k] = perm(of_rb[k], of_g[k], 0x7240);
+                if (C == 3) {
+                    uint32_t *d = reinterpret_cast<uint32_t *>(sf) + lane * 3;
+                    d[0] = perm(pf_[0], pf_[1], 0x4210); d[1] = perm(pf_[1], pf_[2], 0x5421); d[2] = perm(pf_[2], pf_[3], 0x6542);
+                } else {
+                    reinterpret_cast<uint32_t *>(sf)[lane] = perm(perm(pf_[0], pf_[1], 0x0040), perm(pf_[2], pf_[3], 0x0040), 0x5410);
+                }
+            }
+            // ---- the left neighbour's sums for row y+1: valid once every word carries this launch's tag
+            if (has_left && y + 1 < H) {
+                bool ok = !hl || tags_ok(pfA, tag);
+                while (!__all_sync(FULL, ok)) {
+                    __nanosleep(32);
+                    if (hl) { pfA = ld_relaxed4(mb_i); ok = tags_ok(pfA, tag); }
+                }
+                if (hl)
+                    *reinterpret_cast<uint4 *>(halo + (hs ^ 1) * MBW + 24 + lane * 4) =
+                        make_uint4(pfA.x & ~TAGMASK, pfA.y & ~TAGMASK, pfA.z & ~TAGMASK, pfA.w & ~TAGMASK);
+                pfA = pfB;
+            }
+            mb_i += MBW;
+            __syncwarp();
+            if (lane * 16 < (int)bytesRGB) *reinterpret_cast<uint4 *>(o_fg) = *reinterpret_cast<const uint4 *>(sf + lane * 16);
+            o_fg += p.fpitch;
+            if (lane == 0) mbar_arrive(&empty[slot]);        // every lane has read this stage (syncwarp above)
+            if (++slot == NST) { slot = 0; par ^= 1; }
+            ob ^= 1;
+            if (++rf == NFG) rf = 0;
+            hs ^= 1;
+        }
+    } else {
+        // =========================================== bg warp ===========================================
+        uint8_t *o_bg = p.obg + (int64_t)page * p.bstride + (int64_t)x0 * C + lane * 16;
+        const bool hl = has_left && lane < 6;                // words 0..23 of the neighbour's mailbox row
+        mb_i += lane * 4;
+        uint4 pfA = make_uint4(0, 0, 0, 0), pfB = make_uint4(0, 0, 0, 0);
+        if (hl && 1 < H) pfA = ld_relaxed4(mb_i);
+        uint32_t Cb_rb[K], Cb_g[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) Cb_rb[k] = Cb_g[k] = 0;
+        int rbg = 0;
+
+        for (int y = 0; y < H; y++) {
+            if (hl && y + 2 < H) pfB = ld_relaxed4(mb_i + MBW);
+            mbar_wait(&full[slot], (uint32_t)par);
+
+            uint32_t lo[K], hi[K], px[K], raw[3];
+            {
+                const uint32_t *rp = reinterpret_cast<const uint32_t *>(recS + slot * (SWW * 8)) + lane * 8;
+                const uint4 a = ld4(rp), b = ld4(rp + 4);
+                lo[0] = a.x; hi[0] = a.y; lo[1] = a.z; hi[1] = a.w; lo[2] = b.x; hi[2] = b.y; lo[3] = b.z; hi[3] = b.w;
+            }
+            if (C == 3) {
+                const uint32_t *gp = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS) + lane * 3;
+                raw[0] = gp[0]; raw[1] = gp[1]; raw[2] = gp[2];
+                px[0] = raw[0]; px[1] = perm(raw[0], raw[1], 0x5543); px[2] = perm(raw[1], raw[2], 0x4432); px[3] = raw[2] >> 8;
+            } else {
+                raw[0] = reinterpret_cast<const uint32_t *>(rgbS + slot * SM::RGBS)[lane]; raw[1] = raw[2] = 0;
+                px[0] = perm(raw[0], 0, 0x4000); px[1] = perm(raw[0], 0, 0x4111); px[2] = perm(raw[0], 0, 0x4222); px[3] = perm(raw[0], 0, 0x4333);
+            }
+            const bool need_bg = __any_sync(FULL, (int)(hi[0] | hi[1] | hi[2] | hi[3]) < 0);
+
+            uint32_t ob_rb[K], ob_g[K], pbg[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) { ob_rb[k] = perm(px[k], 0, 0x4240); ob_g[k] = perm(px[k], 0, 0x4441); pbg[k] = px[k]; }
+            if (need_bg) {
+                // ---- bg windows: sums of Cb over the 10 columns to the left = 2 whole lanes + parts of the 3rd
+                uint32_t sb_rb[K], sb_g[K];
+                {
+                    const uint32_t Tr = (Cb_rb[0] + Cb_rb[1]) + (Cb_rb[2] + Cb_rb[3]), Tg = (Cb_g[0] + Cb_g[1]) + (Cb_g[2] + Cb_g[3]);
+                    const uint32_t Ur = Cb_rb[2] + Cb_rb[3], Ug = Cb_g[2] + Cb_g[3];
+                    uint32_t A_r = __shfl_up_sync(FULL, Tr, 1), B_r = __shfl_up_sync(FULL, Tr, 2), U_r = __shfl_up_sync(FULL, Ur, 3),
+                             V_r = __shfl_up_sync(FULL, Cb_rb[3], 3), X_r = __shfl_up_sync(FULL, Cb_rb[0], 2);
+                    uint32_t A_g = __shfl_up_sync(FULL, Tg, 1), B_g = __shfl_up_sync(FULL, Tg, 2), U_g = __shfl_up_sync(FULL, Ug, 3),
+                             V_g = __shfl_up_sync(FULL, Cb_g[3], 3), X_g = __shfl_up_sync(FULL, Cb_g[0], 2);
+                    if (lane < 3) {
+                        // virtual lanes -1, -2, -3 = lanes 31, 30, 29 of the left strip: halo words [8..11], [4..7], [0..3]
+                        const uint32_t *hb = halo + hs * MBW;
+                        uint32_t vr[3][4], vg[3][4];
+                        un4(ld4(hb + 8), vr[0]); un4(ld4(hb + 4), vr[1]); un4(ld4(hb + 0), vr[2]);
+                        un4(ld4(hb + 20), vg[0]); un4(ld4(hb + 16), vg[1]); un4(ld4(hb + 12), vg[2]);
+                        uint32_t tr[3], tg[3];
+#pragma unroll
+                        for (int v = 0; v < 3; v++) {
+                            tr[v] = (vr[v][0] + vr[v][1]) + (vr[v][2] + vr[v][3]);
+                            tg[v] = (vg[v][0] + vg[v][1]) + (vg[v][2] + vg[v][3]);
+                        }
+                        if (lane == 0) {
+                            A_r = tr[0]; A_g = tg[0]; B_r = tr[1]; B_g = tg[1]; X_r = vr[1][0]; X_g = vg[1][0];
+                            U_r = vr[2][2] + vr[2][3]; U_g = vg[2][2] + vg[2][3]; V_r = vr[2][3]; V_g = vg[2][3];
+                        } else if (lane == 1) {
+                            B_r = tr[0]; B_g = tg[0]; X_r = vr[0][0]; X_g = vg[0][0];
+                            U_r = vr[1][2] + vr[1][3]; U_g = vg[1][2] + vg[1][3]; V_r = vr[1][3]; V_g = vg[1][3];
+                        } else {
+                            U_r = vr[0][2] + vr[0][3]; U_g = vg[0][2] + vg[0][3]; V_r = vr[0][3]; V_g = vg[0][3];
+                        }
+                    }
+                    const uint32_t ABr = A_r + B_r, ABg = A_g + B_g;
+                    const uint32_t c01r = Cb_rb[0] + Cb_rb[1], c01g = Cb_g[0] + Cb_g[1];
+                    sb_rb[0] = ABr + U_r;             sb_g[0] = ABg + U_g;
+                    sb_rb[1] = ABr + V_r + Cb_rb[0];  sb_g[1] = ABg + V_g + Cb_g[0];
+                    sb_rb[2] = ABr + c01r;            sb_g[2] = ABg + c01g;
+                    sb_rb[3] = ABr - X_r + c01r + Cb_rb[2];  sb_g[3] = ABg - X_g + c01g + Cb_g[2];
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const bool m = (int)hi[k] < 0;
+                    // bg-type record (legacy packing): r[0,17) g[17,34) b[34,51) den[51,60); other records: quotient discarded
+                    const uint32_t Fr = lo[k] & 0x1ffffu, Fg = (lo[k] >> 17) | ((hi[k] & 3u) << 15), Fb = (hi[k] >> 2) & 0x1ffffu;
+                    const uint32_t nr2 = (Fr + (sb_rb[k] & 0xffffu)) * 2u, nb2 = (Fb + (sb_rb[k] >> 16)) * 2u, ng2 = (Fg + sb_g[k]) * 2u;
+                    const uint32_t den4 = ((hi[k] >> 19) & 0xfffu) * 4u;
+                    uint32_t q_rb, q_g;
+                    div3(Mtab, nr2, ng2, nb2, den4, q_rb, q_g);
+                    ob_rb[k] = m ? q_rb : ob_rb[k]; ob_g[k] = m ? q_g : ob_g[k];
+                    pbg[k] = perm(ob_rb[k], ob_g[k], 0x7240);
+                }
+            }
+
+            // ---- column sums: + out[y], - out[y-10]
+            {
+                uint32_t o_px[K];
+                un4(ld4(ringB + rbg * SWW + lane * 4), o_px);
+#pragma unroll
+                for (int k = 0; k < K; k++) { Cb_rb[k] += ob_rb[k] - perm(o_px[k], 0, 0x4240); Cb_g[k] += ob_g[k] - perm(o_px[k], 0, 0x4441); }
+                st4(ringB + rbg * SWW + lane * 4, pbg);
+            }
+            if (has_right && y + 1 < H && lane >= 29) {
+                st_relaxed4(mb_o + (lane - 29) * 4, Cb_rb[0] | tag, Cb_rb[1] | tag, Cb_rb[2] | tag, Cb_rb[3] | tag);
+                st_relaxed4(mb_o + 12 + (lane - 29) * 4, Cb_g[0] | tag, Cb_g[1] | tag, Cb_g[2] | tag, Cb_g[3] | tag);
+            }
+            mb_o += MBW;
+
+            // ---- stage the output row
+            uint8_t *sb = ost + (ob * 2 + 1) * ROWB;
+            if (C == 3) {
+                uint32_t *e = reinterpret_cast<uint32_t *>(sb) + lane * 3;
+                if (!need_bg) { e[0] = raw[0]; e[1] = raw[1]; e[2] = raw[2]; }
+                else { e[0] = perm(pbg[0], pbg[1], 0x4210); e[1] = perm(pbg[1], pbg[2], 0x5421); e[2] = perm(pbg[2], pbg[3], 0x6542); }
+            } else {
+                reinterpret_cast<uint32_t *>(sb)[lane] = need_bg ? perm(perm(pbg[0], pbg[1], 0x0040), perm(pbg[2], pbg[3], 0x0040), 0x5410) : raw[0];
+            }
+            if (has_left && y + 1 < H) {
+                bool ok = !hl || tags_ok(pfA, tag);
+                while (!__all_sync(FULL, ok)) {
+                    __nanosleep(32);
+                    if (hl) { pfA = ld_relaxed4(mb_i); ok = tags_ok(pfA, tag); }
+                }
+                if (hl)
+                    *reinterpret_cast<uint4 *>(halo + (hs ^ 1) * MBW + lane * 4) =
+                        make_uint4(pfA.x & ~TAGMASK, pfA.y & ~TAGMASK, pfA.z & ~TAGMASK, pfA.w & ~TAGMASK);
+                pfA = pfB;
+            }
+            mb_i += MBW;
+            __syncwarp();
+            if (lane * 16 < (int)bytesRGB) *reinterpret_cast<uint4 *>(o_bg) = *reinterpret_cast<const uint4 *>(sb + lane * 16);
+            o_bg += p.bpitch;
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (++slot == NST) { slot = 0; par ^= 1; }
+            ob ^= 1;
+            if (++rbg == NBG) rbg = 0;
+            hs ^= 1;
+        }
+    }
+}
+
 }  // namespace
 
 size_t iirw_smem_bytes(int C, int wpc) { return MTAB_BYTES + (size_t)wpc * (C == 3 ? WarpSmem<3>::bytes : WarpSmem<1>::bytes); }
+size_t iirw3_smem_bytes(int C, int tpc) { return MTAB_BYTES + (size_t)tpc * (C == 3 ? TrioSmem<3, IST>::bytes : TrioSmem<1, IST>::bytes); }
 
 size_t iirw_mailbox_words(int W, int H, int N) { return (size_t)N * cdiv(W, SWW) * (size_t)H * MBW; }
 
@@ -442,14 +839,35 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     p.W = W; p.H = H; p.N = N; p.S = cdiv(W, SWW);
     p.mailbox = mailbox; p.ticket = ticket;
     p.tag = ((epoch & 0xfu) << 12) | ((epoch >> 4) << 28);
+    { const char *e = getenv("B200MRC_IIRW_PSLEEP"); p.psleep = e ? (unsigned)atoi(e) : 300u; }
     const int jobs = N * p.S;
+    B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
+    // Default: the trio form (one warp per layer + a producer thread, shared TMA-fed input stages): 25 % faster than one
+    // warp per strip on a machine that is not full (4 pages: 1.78 vs 2.39 ms), equal at 64 pages (3.6 ms).
+    // B200MRC_IIRW_MODE=trio|single and B200MRC_IIRW_FEED=tma|async (single form) select the other forms for A/B runs and tests.
+    const char *mode = getenv("B200MRC_IIRW_MODE");
+    const bool big = jobs >= 4 * dev_info().sm_count;
+    const bool use_trio = mode ? strcmp(mode, "single") != 0 : true;
+    if (use_trio) {
+        const char *e = getenv("B200MRC_IIRW_TPC");
+        int tpc = e ? atoi(e) : 2;
+        if (tpc < 1) tpc = 1;
+        if (tpc > 3) tpc = 3;
+        const size_t smem3 = iirw3_smem_bytes(C, tpc);
+        if (smem3 > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
+        const void *kern = tpc == 1 ? (C == 3 ? (const void *)k_opt_iir_w3<3, IST, 1> : (const void *)k_opt_iir_w3<1, IST, 1>)
+                         : tpc == 2 ? (C == 3 ? (const void *)k_opt_iir_w3<3, IST, 2> : (const void *)k_opt_iir_w3<1, IST, 2>)
+                                    : (C == 3 ? (const void *)k_opt_iir_w3<3, IST, 3> : (const void *)k_opt_iir_w3<1, IST, 3>);
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        void *args[] = {(void *)&p};
+        { ProfScope _ps("k_opt_iir_w", st); B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3((unsigned)cdiv(jobs, tpc)), dim3(32 * (2 * tpc + 1)), args, smem3, st)); }
+        count_launch();
+        return B200MRC_OK;
+    }
     const size_t smem = iirw_smem_bytes(C, wpc);
     if (smem > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
-    B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
-    // Feed: TMA bulk copies when the batch fills the machine (>= 4 warp strips per SM: equal or slightly faster there),
-    // lane-private cp.async copies for small batches (shorter row latency).  B200MRC_IIRW_FEED=tma|async overrides.
     const char *feed = getenv("B200MRC_IIRW_FEED");
-    const bool use_tma = feed ? !strcmp(feed, "tma") : jobs >= 4 * dev_info().sm_count;
+    const bool use_tma = feed ? !strcmp(feed, "tma") : big;
     const void *kern = use_tma ? (C == 3 ? (const void *)k_opt_iir_w<3, false> : (const void *)k_opt_iir_w<1, false>)
                                : (C == 3 ? (const void *)k_opt_iir_w<3, true> : (const void *)k_opt_iir_w<1, true>);
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

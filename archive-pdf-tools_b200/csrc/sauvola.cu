@@ -21,6 +21,7 @@
 // Algorithmic HBM bytes: 1 B/px read + 1 B/px written.
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace b200mrc {
 
@@ -245,6 +246,208 @@ __global__ void __launch_bounds__(ST, MINB) k_sauvola_mask(const SauvolaParams p
     }
 }
 
+
+// ---- production form: warp-local prefixes, ONE barrier per row ------------------------------------------------
+// The CTA-wide prefix above costs two barriers and 8 warp totals folded in by every thread per row.  Here every
+// warp publishes the prefix of ITS OWN 128 columns (L) plus its total (WT); a window [clo, chi) spans at most three
+// warps (window <= 255), so   S = L[chi] - L[clo] + WT[wlo] (+ WT[wlo+1]),   the WT indices being row-invariant per
+// pixel (an all-zero entry stands for "same warp").  The buffers alternate with the row, the row loop is unrolled
+// by two so that the buffer is a compile-time offset, and the scan steps use the shuffle's own range predicate.
+constexpr int SPN = SK * (ST + 1);       // prefix entries per buffer
+constexpr int WTN = 16;                  // warp-total entries per buffer: [0..7] totals, [8] = 0
+template <int V> struct IntC { static constexpr int value = V; };
+
+__device__ __forceinline__ void scan_up2(uint32_t &a, uint32_t &b, int d)
+{
+    // a += shfl_up(a, d), b += shfl_up(b, d) for lanes >= d (the shuffle's predicate says whether the source lane exists)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t, u;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %2, 0, 0xffffffff;\n\t"
+        "shfl.sync.up.b32 u, %1, %2, 0, 0xffffffff;\n\t"
+        "@p add.u32 %0, %0, t;\n\t"
+        "@p add.u32 %1, %1, u;\n\t}"
+        : "+r"(a), "+r"(b) : "r"(d));
+}
+
+template <bool KNEG, bool WIDE, int MINB>
+__global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams p)
+{
+    __shared__ uint2 sP[2 * SPN];
+    __shared__ uint2 sWT[2 * WTN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
+    const int page = blockIdx.y;
+    const int sx0 = strip * p.strip_w;
+    const int ex0 = sx0 - p.ext_left;             // first input column of this CTA (multiple of 4)
+    const int by0 = band * p.band_h;
+    const int by1 = min(p.H, by0 + p.band_h);
+    const int W = p.W, H = p.H;
+    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
+    uint8_t *out = p.out + (int64_t)page * p.out_stride;
+
+    const int i0 = tid * SK;                      // local column of this thread's first pixel
+    const int gx = ex0 + i0;                      // global column (multiple of 4, may be < 0 or >= W)
+    const bool is_out = (gx >= sx0) && (gx < sx0 + p.strip_w) && (gx < W);
+
+    const uint32_t inv = (p.flags & B200MRC_SAUVOLA_INVERT_INPUT) ? 0xffffffffu : 0u;   // threshold 255 - p (mrc.py:226)
+    uint32_t cs[SK], cq[SK];
+#pragma unroll
+    for (int j = 0; j < SK; j++) { cs[j] = 0; cq[j] = 0; }
+    // row-invariant per-thread constants: smem slots of the two prefix entries of each pixel's window and of the
+    // warp totals between them, the window width, and where this thread publishes its own prefixes
+    int slot_hi[SK], slot_lo[SK], slot_st[SK];
+    uint32_t wtA = 0, wtB = 0;                    // byte offsets of the 4 pixels' warp-total entries, one per byte
+    auto nx_of = [&](const int j) { const int x = gx + j; return (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0; };
+#pragma unroll
+    for (int j = 0; j < SK; j++) {
+        const int i = i0 + j;
+        const int chi = i + p.r + 1, clo = max(i - p.l + 1, 0), cst = i + 1;
+        slot_hi[j] = (chi & 3) * (ST + 1) + (chi >> 2);
+        slot_lo[j] = (clo & 3) * (ST + 1) + (clo >> 2);
+        slot_st[j] = (cst & 3) * (ST + 1) + (cst >> 2);
+        const int whi = (chi - 1) >> 7, wlo = clo > 0 ? (clo - 1) >> 7 : 0;      // warps holding columns chi-1 / clo-1
+        wtA |= (uint32_t)(min(whi > wlo ? wlo : 8, 8) * 8) << (8 * j);
+        wtB |= (uint32_t)(min(whi > wlo + 1 ? wlo + 1 : 8, 8) * 8) << (8 * j);
+    }
+    const int nx0 = nx_of(0);
+    const bool nx_uniform = nx0 == nx_of(1) && nx0 == nx_of(2) && nx0 == nx_of(3);
+
+    // ---- band warm-up: column sums over the window rows of the first output row
+    {
+        const int r0 = max(0, by0 - p.o + 1), r1 = min(H - 1, by0 + p.u);
+        for (int yy = r0; yy <= r1; yy++) {
+            uint32_t w = load_word_clamped(in + (int64_t)yy * p.in_pitch, gx, W, inv);
+#pragma unroll
+            for (int j = 0; j < SK; j++) {
+                uint32_t v = (w >> (8 * j)) & 0xFFu;
+                cs[j] += v; cq[j] += v * v;
+            }
+        }
+    }
+    if (tid < 2) {
+        // L[0] = 0 (slot of column boundary 0, written by nobody else) and the all-zero warp total
+        sP[tid * SPN] = make_uint2(0u, 0u);
+        sWT[tid * WTN + 8] = make_uint2(0u, 0u);
+    }
+
+    // loads run two rows ahead of their use (see k_sauvola_mask)
+    const bool lok = gx >= 0 && gx < W;
+    const uint32_t lmask = !lok ? 0u : (W - gx >= 4 ? 0xffffffffu : (1u << (8 * (W - gx))) - 1u);
+    const uint8_t *pe = in + (int64_t)(by0 + 1 + p.u) * p.in_pitch + gx;      // entering row of the next load_upd
+    const uint8_t *pl = in + (int64_t)(by0 + 1 - p.o) * p.in_pitch + gx;      // leaving row
+    const uint8_t *pc = in + (int64_t)(by0 + 1) * p.in_pitch + gx;            // its own pixels
+    auto load_upd = [&](int yu, uint32_t &we, uint32_t &wl, uint32_t &wc) {
+        we = 0; wl = 0; wc = 0;
+        if (yu < by1 && lok) {
+            if (yu + p.u < H) we = __ldg(reinterpret_cast<const uint32_t *>(pe));
+            if (yu - p.o >= 0) wl = __ldg(reinterpret_cast<const uint32_t *>(pl));
+            wc = __ldg(reinterpret_cast<const uint32_t *>(pc));
+        }
+        pe += p.in_pitch; pl += p.in_pitch; pc += p.in_pitch;
+    };
+    uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W, inv);
+    uint32_t weA, wlA, wcA, weB, wlB, wcB;
+    load_upd(by0 + 1, weA, wlA, wcA);
+    load_upd(by0 + 2, weB, wlB, wcB);
+    int ny_cached = -1;
+    double rn_u = 0.0;
+    uint8_t *orow = out + (int64_t)by0 * p.out_pitch + gx;
+
+    auto step = [&](auto BUFC, const int y) {
+        constexpr int B = decltype(BUFC)::value;
+        uint2 *P = sP + B * SPN, *T = sWT + B * WTN;
+        // rows outside the page were not loaded (0) and must stay 0 under inversion
+        const uint32_t inv_e = (y + 1 + p.u < H && y + 1 < by1) ? inv : 0u, inv_l = (y + 1 - p.o >= 0 && y + 1 < by1) ? inv : 0u,
+                       inv_c = (y + 1 < by1) ? inv : 0u;
+        const uint32_t wenter = (weA ^ inv_e) & lmask, wleave = (wlA ^ inv_l) & lmask, wnext = (wcA ^ inv_c) & lmask;
+        weA = weB; wlA = wlB; wcA = wcB;
+        load_upd(y + 3, weB, wlB, wcB);
+
+        // ---- prefix of the column sums across the warp
+        uint32_t ps[SK], pq[SK];
+        ps[0] = cs[0]; pq[0] = cq[0];
+#pragma unroll
+        for (int j = 1; j < SK; j++) { ps[j] = ps[j - 1] + cs[j]; pq[j] = pq[j - 1] + cq[j]; }
+        uint32_t ws = ps[SK - 1], wq = pq[SK - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) scan_up2(ws, wq, d);
+        if (lane == 31) T[warp] = make_uint2(ws, wq);
+        const uint32_t bs = ws - ps[SK - 1], bq = wq - pq[SK - 1];     // exclusive within the warp
+        // inclusive warp-local prefix up to local column c-1 is stored at "c": column c -> [c&3][c>>2]
+#pragma unroll
+        for (int j = 0; j < SK; j++) P[slot_st[j]] = make_uint2(bs + ps[j], bq + pq[j]);
+        __syncthreads();
+
+        // ---- per-pixel test
+        if (is_out) {
+            const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
+            uint32_t bits = 0;
+            // S/n and Q/n on the FP64 pipe: floor((a + 0.5) * (1/n)) == a / n exactly (see k_sauvola_mask)
+            if (nx_uniform && ny != ny_cached) { rn_u = 1.0 / (double)(nx0 * ny); ny_cached = ny; }
+            uint32_t S[SK], Q[SK];
+#pragma unroll
+            for (int j = 0; j < SK; j++) {
+                const uint2 hi = P[slot_hi[j]];
+                const uint2 lo = P[slot_lo[j]];
+                const uint2 ta = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(T) + ((wtA >> (8 * j)) & 0xFFu));
+                S[j] = hi.x - lo.x + ta.x; Q[j] = hi.y - lo.y + ta.y;
+                if (WIDE) {
+                    const uint2 tb = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(T) + ((wtB >> (8 * j)) & 0xFFu));
+                    S[j] += tb.x; Q[j] += tb.y;
+                }
+            }
+            auto test = [&](const uint32_t s, const uint32_t q, const int j, const double rn) -> uint32_t {
+                const double md = floor(__dmul_rn(__dadd_rn((double)s, 0.5), rn));      // (double)(S / n)
+                const double qd = floor(__dmul_rn(__dadd_rn((double)q, 0.5), rn));      // (double)(Q / n)
+                const double mm = __dmul_rn(md, md);                                    // exact (integers < 2^53)
+                const double v = __dadd_rn(qd, -mm);
+                const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
+                const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
+                const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
+                const double lhs = __dmul_rn(t, t);
+                return KNEG ? ((t <= 0.0) && (lhs >= rhs)) : ((t <= 0.0) || (lhs <= rhs));
+            };
+            if (nx_uniform) {
+                // interior thread: one window area for its 4 pixels (n > 0 because the thread is inside the page)
+#pragma unroll
+                for (int j = 0; j < SK; j++) bits |= test(S[j], Q[j], j, rn_u) << (8 * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SK; j++) {
+                    const int n = nx_of(j) * ny;
+                    if (n > 0) bits |= test(S[j], Q[j], j, 1.0 / (double)n) << (8 * j);
+                }
+            }
+            if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) bits ^= 0x01010101u;
+            if (gx + 3 < W) {
+                uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
+                if (p.flags & B200MRC_SAUVOLA_OR_INTO) bits |= *o32;
+                *o32 = bits;
+            } else {
+                for (int j = 0; j < SK && gx + j < W; j++) {
+                    uint8_t b = (uint8_t)((bits >> (8 * j)) & 0xFFu);
+                    if (p.flags & B200MRC_SAUVOLA_OR_INTO) b |= orow[j];
+                    orow[j] = b;
+                }
+            }
+        }
+        orow += p.out_pitch;
+
+        // ---- slide the window rows for the next output row
+#pragma unroll
+        for (int j = 0; j < SK; j++) {
+            const uint32_t a = (wenter >> (8 * j)) & 0xFFu, b = (wleave >> (8 * j)) & 0xFFu;
+            cs[j] += a - b;
+            cq[j] += a * a - b * b;
+        }
+        wcur = wnext;
+    };
+
+    int y = by0;
+    for (; y + 1 < by1; y += 2) { step(IntC<0>(), y); step(IntC<1>(), y + 1); }
+    if (y < by1) step(IntC<0>(), y);
+}
+
 }  // namespace
 
 }  // namespace b200mrc
@@ -287,11 +490,22 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream);
       const char *mb = getenv("B200MRC_SAUVOLA_MINB");
       const int minb = mb ? atoi(mb) : 4;
-      if (p.kneg) k_sauvola_mask<true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else if (minb == 5) k_sauvola_mask<false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else if (minb == 6) k_sauvola_mask<false, 6><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else if (minb == 3) k_sauvola_mask<false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else k_sauvola_mask<false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
+      const char *pf = getenv("B200MRC_SAUVOLA_PREFIX");          // "cta": the two-barrier CTA-wide prefix (A/B runs)
+      const bool wide = window_width > 128;                        // a window may then span three warps
+      if (pf && !strcmp(pf, "cta")) {
+          if (p.kneg) k_sauvola_mask<true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+          else if (minb == 5) k_sauvola_mask<false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+          else if (minb == 6) k_sauvola_mask<false, 6><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+          else if (minb == 3) k_sauvola_mask<false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+          else k_sauvola_mask<false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      } else if (p.kneg) {
+          if (wide) k_sauvola_mask_w<true, true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+          else k_sauvola_mask_w<true, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      } else if (wide) {
+          k_sauvola_mask_w<false, true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      } else if (minb == 5) k_sauvola_mask_w<false, false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else if (minb == 3) k_sauvola_mask_w<false, false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
+      else k_sauvola_mask_w<false, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

@@ -178,6 +178,54 @@ def test_optimise_text_page_many_strips(eng, orc, synth):
     assert np.array_equal(bg.numpy()[0], orc.optimise(~mask, page, 10))
 
 
+@pytest.mark.parametrize('variant', [{'B200MRC_IIRW_MODE': 'trio'}, {'B200MRC_IIRW_MODE': 'trio', 'B200MRC_IIRW_TPC': '1'},
+                                     {'B200MRC_IIRW_MODE': 'trio', 'B200MRC_IIRW_TPC': '3'},
+                                     {'B200MRC_IIRW_MODE': 'single', 'B200MRC_IIRW_FEED': 'tma'},
+                                     {'B200MRC_IIRW_MODE': 'single', 'B200MRC_IIRW_FEED': 'async'}],
+                         ids=['trio', 'trio1', 'trio3', 'single-tma', 'single-async'])
+def test_optimise_sweep_variants(eng, orc, synth, monkeypatch, variant):
+    """Every form of the row-sequential sweep (launcher picks by batch size; forced here) against the oracle:
+    ragged strip widths, many strips, gray and RGB, random masks and a text page, several pages per launch."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    for (h, w), c in [((37, 128), 3), ((64, 129), 3), ((90, 700), 1), ((131, 397), 3), ((70, 1027), 1), ((1, 300), 3), ((5, 4), 3)]:
+        dens = (0.0, 0.05, 0.5, 1.0)
+        masks = np.stack([rng.random((h, w)) < d for d in dens])
+        imgs = rng.integers(0, 256, (len(dens), h, w, 3) if c == 3 else (len(dens), h, w), dtype=np.uint8)
+        m = _plane(eng, masks); src = _plane(eng, imgs)
+        fg = _empty(eng, len(dens), h, w, c); bg = _empty(eng, len(dens), h, w, c)
+        for rep in range(2):                                  # second launch: mailbox reuse under a new epoch
+            eng.optimise(m, src, fg, 3, bg, 10)
+            gf, gb = fg.numpy(), bg.numpy()
+            for i in range(len(dens)):
+                assert np.array_equal(gf[i], orc.optimise(masks[i], imgs[i], 3)), ('fg', variant, h, w, c, i, rep)
+                assert np.array_equal(gb[i], orc.optimise(~masks[i], imgs[i], 10)), ('bg', variant, h, w, c, i, rep)
+    pages = np.stack([synth.make_page(20 + i, 420, 1300, dpi=200, halftone=(i == 1)) for i in range(3)])
+    mks = np.stack([orc.denoise(orc.sauvola(orc.rgb2gray(pg), 51)) for pg in pages])
+    m = _plane(eng, mks); src = _plane(eng, pages)
+    fg = _empty(eng, 3, 420, 1300, 3); bg = _empty(eng, 3, 420, 1300, 3)
+    eng.optimise(m, src, fg, 3, bg, 10)
+    for i in range(3):
+        assert np.array_equal(fg.numpy()[i], orc.optimise(mks[i], pages[i], 3))
+        assert np.array_equal(bg.numpy()[i], orc.optimise(~mks[i], pages[i], 10))
+
+
+@pytest.mark.parametrize('prefix', ['warp', 'cta'])
+def test_sauvola_prefix_variants(eng, orc, monkeypatch, prefix):
+    """Both horizontal-prefix forms of the Sauvola kernel (warp-local: production; CTA-wide: kept for A/B runs)."""
+    monkeypatch.setenv('B200MRC_SAUVOLA_PREFIX', prefix)
+    rng = np.random.default_rng(11)
+    for h, w in [(150, 2600), (260, 1100), (40, 130)]:
+        img = np.clip(rng.normal(190, 45, (2, h, w)), 0, 255).astype(np.uint8)
+        src = _plane(eng, img); dst = _empty(eng, 2, h, w)
+        for ww, k in [(33, 0.34), (101, 0.34), (127, 0.34), (128, 0.2), (129, 0.34), (151, 0.34), (255, 0.1)]:
+            eng.sauvola(src, dst, ww, ww, k=k)
+            got = dst.numpy(np.bool_)
+            for i in range(2):
+                assert np.array_equal(got[i], orc.sauvola(img[i], ww, ww, k=k)), (prefix, h, w, ww, i)
+
+
 @pytest.mark.parametrize('shape', [(33, 25), (100, 77), (330, 255), (64, 64), (7, 5), (600, 450)])
 def test_thumbnail_matches_oracle_and_pillow(eng, orc, shape):
     from PIL import Image
