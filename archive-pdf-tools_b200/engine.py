@@ -400,12 +400,23 @@ class StreamedDecomposer:
     def run(self, host_pages, out, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST):
         """host_pages: CPU uint8 tensor [N,H,W(,C)]; out: dict from alloc_outputs().  Returns after
         everything has landed in `out` (one final stream synchronisation)."""
+        self.run_async(host_pages, out, window, k, R, denoise_mask).synchronize()
+        torch.cuda.current_stream().wait_stream(self.s_out)
+        return out
+
+    def run_async(self, host_pages, out, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST):
+        """Enqueue one batch and return the CUDA event that fires when its last result byte is in `out`.
+        Calls may follow each other without waiting (a book is a stream of batches): the H2D copies and kernels
+        of the next batch then overlap the D2H tail of this one.  Every call in flight needs its own `out`;
+        `host_pages` must stay untouched until the event has fired."""
         n, ck, nb = self.n, self.chunk, self.nb
         hp = host_pages.reshape(n, self.h, self.w * self.c)
         assert hp.is_contiguous() and hp.dtype == torch.uint8
         cur = torch.cuda.current_stream()
         for s in [self.s_in, self.s_out] + self.s_cmp:
             s.wait_stream(cur)
+        # last users of every device buffer slot, carried over from the previous call
+        tail_cmp, tail_out = getattr(self, '_tail_cmp', {}), getattr(self, '_tail_out', {})
         in_done, cmp_done, out_done = {}, {}, {}
         n_chunks = (n + ck - 1) // ck
         names = ('mask',) if self.mask_only else ('mask', 'fg', 'bg')
@@ -414,17 +425,19 @@ class StreamedDecomposer:
             m = hi - lo
             slot = i % nb
             b = self.batches[slot]
-            sc = self.s_cmp[i % len(self.s_cmp)]
+            sc = self.s_cmp[slot % len(self.s_cmp)]
             st_in = self.st_in[slot]
+            prev_cmp = cmp_done.get(i - nb, tail_cmp.get(slot))
+            prev_out = out_done.get(i - nb, tail_out.get(slot))
             with torch.cuda.stream(self.s_in):
-                if i >= nb:
-                    self.s_in.wait_event(cmp_done[i - nb])         # input staging / img plane of this slot is free again
+                if prev_cmp is not None:
+                    self.s_in.wait_event(prev_cmp)                 # input staging / img plane of this slot is free again
                 (st_in if st_in is not None else b.img.t)[:m].copy_(hp[lo:hi], non_blocking=True)
                 in_done[i] = self.s_in.record_event()
             with torch.cuda.stream(sc):
                 sc.wait_event(in_done[i])
-                if i >= nb:
-                    sc.wait_event(out_done[i - nb])                # output staging of this slot was drained
+                if prev_out is not None:
+                    sc.wait_event(prev_out)                        # output staging of this slot was drained
                 if st_in is not None:
                     row = self.w * self.c
                     _copy2d(b.img.t.data_ptr(), b.img.pitch, st_in.data_ptr(), row, row, m * self.h, L.COPY_D2D, sc)
@@ -441,6 +454,6 @@ class StreamedDecomposer:
                     plane, st = getattr(b, name), self.st_out[slot][name]
                     out[name][lo:hi].copy_((st if st is not None else plane.t)[:m], non_blocking=True)
                 out_done[i] = self.s_out.record_event()
-        cur.wait_stream(self.s_out)
-        self.s_out.synchronize()
-        return out
+            tail_cmp[slot], tail_out[slot] = cmp_done[i], out_done[i]
+        self._tail_cmp, self._tail_out = tail_cmp, tail_out
+        return out_done[n_chunks - 1]

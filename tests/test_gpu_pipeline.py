@@ -178,6 +178,30 @@ def test_streamed_decomposer_matches_batched(eng, synth):
         assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg']), kw
 
 
+def test_streamed_decomposer_back_to_back_calls(eng, synth):
+    """run_async: several batches in flight (no wait between calls, own result buffers each) give the same bytes
+    as one call at a time; buffer slots are handed from call to call by events."""
+    import torch
+    import archive_pdf_tools_b200 as pkg
+    from archive_pdf_tools_b200.engine import StreamedDecomposer
+    sets = [np.stack([synth.make_page(400 + 10 * j + i, 270, 330, dpi=100, sigma_n=3.0, halftone=(i == 1)) for i in range(5)]) for j in range(3)]
+    refs = [pkg.decompose_pages(pg, dpi=100, bg_downsample=3, denoise_mask='fast') for pg in sets]
+    hosts = [torch.from_numpy(pg).pin_memory() for pg in sets]
+    for kw in (dict(chunk=2), dict(chunk=1, buffers=3, compute_streams=3), dict(chunk=5)):
+        sd = StreamedDecomposer(eng, 5, 270, 330, 3, bg_downsample=3, **kw)
+        outs = [sd.alloc_outputs() for _ in range(3)]
+        for rep in range(2):
+            for o in outs:
+                for v in o.values():
+                    v.zero_()
+            evs = [sd.run_async(hosts[j], outs[j], 25, denoise_mask='fast') for j in range(3)]
+            for j in (2, 0, 1):
+                evs[j].synchronize()
+                assert np.array_equal(outs[j]['mask'].numpy().astype(bool), refs[j]['mask']), (kw, rep, j)
+                assert np.array_equal(outs[j]['fg'].numpy().reshape(refs[j]['fg'].shape), refs[j]['fg']), (kw, rep, j)
+                assert np.array_equal(outs[j]['bg'].numpy().reshape(refs[j]['bg'].shape), refs[j]['bg']), (kw, rep, j)
+
+
 def test_copy2d_roundtrip(eng):
     """b200mrc_copy2d: pitched H2D / D2D / D2H of a batch of pages keeps every byte, touches no padding."""
     import ctypes as C
