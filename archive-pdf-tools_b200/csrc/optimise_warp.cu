@@ -842,12 +842,16 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     { const char *e = getenv("B200MRC_IIRW_PSLEEP"); p.psleep = e ? (unsigned)atoi(e) : 300u; }
     const int jobs = N * p.S;
     B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
-    // Default: the trio form (one warp per layer + a producer thread, shared TMA-fed input stages): 25 % faster than one
-    // warp per strip on a machine that is not full (4 pages: 1.78 vs 2.39 ms), equal at 64 pages (3.6 ms).
-    // B200MRC_IIRW_MODE=trio|single and B200MRC_IIRW_FEED=tma|async (single form) select the other forms for A/B runs and tests.
+    // Which form (measured on B200, 3300x2550 RGB pages, ms per launch; profiles/r1q_ab_sweep.txt):
+    //   pages        4      16     32     64
+    //   one warp     2.39   2.44   2.97   3.59      (45 % of the issue slots at 64 pages)
+    //   trio         1.78   2.17   2.51   3.60      (62 %: a second batch on another stream overlaps less)
+    // The trio form (one warp per layer + a producer thread, shared TMA-fed stages) wins while the machine is not full;
+    // from ~6 strips per SM on the one-warp form is as fast and leaves more room for concurrent kernels.
+    // B200MRC_IIRW_MODE=trio|single and B200MRC_IIRW_FEED=tma|async (single form) override for A/B runs and tests.
     const char *mode = getenv("B200MRC_IIRW_MODE");
-    const bool big = jobs >= 4 * dev_info().sm_count;
-    const bool use_trio = mode ? strcmp(mode, "single") != 0 : true;
+    const bool big = jobs >= 6 * dev_info().sm_count;
+    const bool use_trio = mode ? strcmp(mode, "single") != 0 : !big;
     if (use_trio) {
         const char *e = getenv("B200MRC_IIRW_TPC");
         int tpc = e ? atoi(e) : 2;
