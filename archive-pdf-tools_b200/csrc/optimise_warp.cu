@@ -21,6 +21,9 @@
 //   * column sums live in registers in 16-bit lanes (r | b << 16, g); the last n output rows are
 //     smem rings private to each lane (no synchronisation); rows without a mask pixel in the strip
 //     (the common case) take a short path: fg = quotient, bg = copy of the input row.
+// Two forms share the arithmetic and the mailbox protocol (launch_opt_iir_warp picks by batch size): k_opt_iir_w, one
+// warp per strip as described above, and k_opt_iir_w3 (further down), where the two layers of a strip run on two warps
+// fed by a producer thread -- shorter row steps for machines that are not full.
 // The truncating division is one multiply-high: floor(num/den) = umulhi(2*num, ceil(2^31/den)),
 // exact for num <= 255*den, den <= 500; records of fg pixels arrive pre-doubled in 16-bit lanes
 // (optimise_firw.cu) so that numerator assembly is one multiply-add per word.

@@ -13,8 +13,10 @@
 //     (sum, sum of squares over the window's rows) in registers; per output row it adds the
 //     entering row and subtracts the leaving row (32-bit vector loads, L2-resident re-reads);
 //   * the horizontal window sum is a difference of two entries of the per-row prefix of the
-//     column sums: thread-local prefix -> warp-shuffle inclusive scan -> 8 warp totals in smem;
-//     prefixes are published in a bank-conflict-free SoA layout (column c -> [c&3][c>>2]);
+//     column sums: thread-local prefix -> warp-shuffle inclusive scan; prefixes are published in a
+//     bank-conflict-free SoA layout (column c -> [c&3][c>>2]).  Production form (k_sauvola_mask_w):
+//     the published prefixes are warp-local and a pixel adds the totals of the warps between its two
+//     entries -> one CTA barrier per row.  A/B form (k_sauvola_mask): CTA-wide prefixes, two barriers;
 //   * uint32 wrap-around arithmetic is exact because every window sum is < 2^32 for w <= 255;
 //   * S/n and Q/n are exact floors computed on the FP64 pipe (floor((a+0.5)*(1/n))); the test runs in
 //     FP64 with __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
