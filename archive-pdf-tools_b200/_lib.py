@@ -44,12 +44,17 @@ PROTOTYPES = {
     'b200mrc_version': (C.c_int, []),
     'b200mrc_error_string': (C.c_char_p, [C.c_int]),
     'b200mrc_launch_count': (C.c_uint64, []),
+    'b200mrc_set_tuning': (C.c_int, [C.c_char_p, C.c_int]),
+    'b200mrc_get_tuning': (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     'b200mrc_profile_enable': (C.c_int, [C.c_int]),
     'b200mrc_profile_report': (C.c_int, [C.c_char_p, C.c_size_t]),
     'b200mrc_copy2d': (C.c_int, [vp, i64, vp, i64, i64, i64, C.c_int, vp]),
     'b200mrc_rgb2gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp]),
     'b200mrc_sauvola': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, vp]),
+    'b200mrc_threshold_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    'b200mrc_threshold_mask': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_double, C.c_double, vp, C.c_int, vp, C.c_size_t, vp]),
     'b200mrc_noise_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'b200mrc_estimate_noise': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
     'b200mrc_gray_blur': (C.c_int, [vp, i64, i64, C.c_int, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
@@ -100,6 +105,23 @@ def check(status, what=''):
     if status != 0:
         msg = lib().b200mrc_error_string(status)
         raise B200MrcError('%s failed (%d): %s' % (what or 'b200mrc call', status, msg.decode() if msg else '?'))
+
+
+TUNING_WORDS = {'single': 1, 'trio': 2, 'tma': 1, 'async': 2, 'legacy': 1, 'generic': 1, 'fused': 0, 'split': 0, 'auto': 0}
+
+
+def set_tuning(name, value):
+    """b200mrc_set_tuning: name without the B200MRC_ prefix (e.g. 'IIRW_MODE'); value an int or one of the words the
+    environment variable accepts ('single', 'trio', 'tma', 'async', 'legacy', 'generic', 'auto')."""
+    if isinstance(value, str):
+        value = TUNING_WORDS[value] if value in TUNING_WORDS else int(value)
+    check(lib().b200mrc_set_tuning(name.encode(), int(value)), 'b200mrc_set_tuning(%s)' % name)
+
+
+def get_tuning(name):
+    v = C.c_int(0)
+    check(lib().b200mrc_get_tuning(name.encode(), C.byref(v)), 'b200mrc_get_tuning(%s)' % name)
+    return v.value
 
 
 def profile_enable(on=True):

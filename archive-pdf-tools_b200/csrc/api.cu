@@ -10,7 +10,10 @@
 #include "common.cuh"
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,22 +25,65 @@ std::atomic<uint64_t> g_launch_count{0};
 
 namespace {
 struct ProfRec { const char *name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;                   // guards g_prof (launches may come from several host threads)
 std::vector<ProfRec> g_prof;
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
 }  // namespace
 
-void prof_begin(const char *kernel, cudaStream_t st)
+// A ProfScope holds the index of its own record, so scopes of different threads do not mix their end events.
+int prof_begin(const char *kernel, cudaStream_t st)
 {
-    if (!g_prof_on) return;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return -1;
     ProfRec r{kernel, nullptr, nullptr};
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
 }
-void prof_end(cudaStream_t st)
+void prof_end(int idx, cudaStream_t st)
 {
-    if (!g_prof_on || g_prof.empty()) return;
-    cudaEventRecord(g_prof.back().b, st);
+    if (idx < 0) return;
+    cudaEvent_t b = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (idx < (int)g_prof.size()) b = g_prof[idx].b;
+    }
+    if (b) cudaEventRecord(b, st);
+}
+
+namespace {
+struct TuneDef { const char *name; int dflt; const char *word1, *word2; };      // env strings word1 -> 1, word2 -> 2
+const TuneDef k_tune_defs[T_COUNT] = {
+    {"IIRW_MODE", 0, "single", "trio"}, {"IIRW_TPC", 2, nullptr, nullptr}, {"IIRW_FEED", 0, "tma", "async"},
+    {"IIRW_PSLEEP", 300, nullptr, nullptr}, {"IIRW_WPC", 2, nullptr, nullptr}, {"FIRW_BAND", 256, nullptr, nullptr},
+    {"FIRW_WPC", 4, nullptr, nullptr}, {"FUSED_NT", 0, nullptr, nullptr}, {"FUSED_BANDS", 0, nullptr, nullptr},
+    {"THRESHOLD_PATH", 0, "legacy", nullptr}, {"OPT_PATH", 0, "generic", nullptr}, {"NOISE_DIRECT", 0, nullptr, nullptr},
+    {"RESAMPLE_2PASS", 0, nullptr, nullptr}, {"TILE_H", 32, nullptr, nullptr}, {"DECOMPOSE_GROUPS", 0, nullptr, nullptr},
+    {"DECOMPOSE_STREAMS", 0, nullptr, nullptr},
+};
+std::atomic<int> g_tune[T_COUNT];
+std::once_flag g_tune_once;
+void tune_init()
+{
+    for (int i = 0; i < T_COUNT; i++) {
+        const TuneDef &d = k_tune_defs[i];
+        int v = d.dflt;
+        const std::string env = std::string("B200MRC_") + d.name;
+        if (const char *e = getenv(env.c_str())) {
+            if (d.word1 && !strcmp(e, d.word1)) v = 1;
+            else if (d.word2 && !strcmp(e, d.word2)) v = 2;
+            else v = atoi(e);
+        }
+        g_tune[i].store(v);
+    }
+}
+}  // namespace
+
+int tune(TuneKey k)
+{
+    std::call_once(g_tune_once, tune_init);
+    return g_tune[k].load(std::memory_order_relaxed);
 }
 
 const DevInfo &dev_info()
@@ -74,10 +120,59 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
 
 namespace {
 
+// A batch is split into page groups that run on internal streams: the row-latency-bound sweep of one group overlaps the
+// issue-bound stages of the others (measured: profiles/).  The tuning keys DECOMPOSE_GROUPS /
+// DECOMPOSE_STREAMS override the choice.
+constexpr int MAX_INTERNAL_STREAMS = 4;
+struct GroupPlan { int groups, per_group, streams; };
+
+GroupPlan group_plan(int N)
+{
+    const int env_groups = tune(T_DECOMPOSE_GROUPS), env_streams = tune(T_DECOMPOSE_STREAMS);
+    int g = env_groups > 0 ? env_groups : (N >= 32 ? 4 : (N >= 8 ? 2 : 1));
+    if (g > N) g = N;
+    GroupPlan gp;
+    gp.per_group = (N + g - 1) / g;
+    gp.groups = (N + gp.per_group - 1) / gp.per_group;
+    gp.streams = env_streams > 0 ? env_streams : (gp.groups >= 4 ? 3 : gp.groups);
+    if (gp.streams > MAX_INTERNAL_STREAMS) gp.streams = MAX_INTERNAL_STREAMS;
+    if (gp.streams > gp.groups) gp.streams = gp.groups;
+    if (gp.groups == 1) gp.streams = 0;                  // the caller's stream
+    return gp;
+}
+
+struct DevStreams {
+    bool ready = false;
+    cudaStream_t s[MAX_INTERNAL_STREAMS];
+    cudaEvent_t ev_in, ev_done[MAX_INTERNAL_STREAMS];
+};
+std::mutex g_streams_mu;
+DevStreams g_streams[64];
+
+int internal_streams(DevStreams **out)
+{
+    int dev = 0;
+    B200MRC_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return B200MRC_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_streams_mu);
+    DevStreams &d = g_streams[dev];
+    if (!d.ready) {
+        for (int i = 0; i < MAX_INTERNAL_STREAMS; i++) {
+            B200MRC_CUDA_TRY(cudaStreamCreateWithFlags(&d.s[i], cudaStreamNonBlocking));
+            B200MRC_CUDA_TRY(cudaEventCreateWithFlags(&d.ev_done[i], cudaEventDisableTiming));
+        }
+        B200MRC_CUDA_TRY(cudaEventCreateWithFlags(&d.ev_in, cudaEventDisableTiming));
+        d.ready = true;
+    }
+    *out = &d;
+    return B200MRC_OK;
+}
+
 struct DecomposeLayout {
     size_t gray_pitch, gray_page;
     size_t full_pitch, full_page;          // full-resolution fg / bg planes when downsampled
-    size_t off_sigma, off_gray, off_fgfull, off_bgfull, off_scratch, scratch_bytes, total;
+    GroupPlan gp;
+    size_t off_sigma, off_gray, off_fgfull, off_bgfull, off_scratch, scratch_bytes, off_opt, opt_bytes, total;
 };
 
 DecomposeLayout decompose_layout(const b200mrc_decompose_args *a)
@@ -86,23 +181,29 @@ DecomposeLayout decompose_layout(const b200mrc_decompose_args *a)
     memset(&L, 0, sizeof(L));
     const int W = a->width, H = a->height, N = a->n_pages, C = a->channels;
     const bool mask_only = (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) != 0;
+    L.gp = group_plan(N);
+    const int n = L.gp.per_group;
     L.gray_pitch = align_up((size_t)W, 16); L.gray_page = L.gray_pitch * H;
     L.full_pitch = align_up((size_t)W * C, 16); L.full_page = L.full_pitch * H;
     Carver c;
     L.off_sigma = c.take<double>(N);
-    L.off_gray = c.take<uint8_t>(L.gray_page * N);
+    L.off_gray = c.take<uint8_t>(L.gray_page * N + 256);     // the threshold's gray delay line (sauvola_fused.cu)
     if (!mask_only && a->fg_plan) L.off_fgfull = c.take<uint8_t>(L.full_page * N);
     if (!mask_only && a->bg_plan) L.off_bgfull = c.take<uint8_t>(L.full_page * N);
-    // stages run one after another on the stream: they share one scratch region
-    size_t s = noise_workspace_bytes(W, H, N);
-    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) s = std::max(s, denoise_workspace_bytes(W, H, N));
+    // per group: one scratch region shared by the stages that run one after another on the group's stream ...
+    size_t s = noise_workspace_bytes(W, H, n);
+    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) s = std::max(s, denoise_workspace_bytes(W, H, n));
     if (!mask_only) {
-        s = std::max(s, optimise_workspace_bytes(W, H, N));
-        if (a->fg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->fg_plan, N));
-        if (a->bg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->bg_plan, N));
+        if (a->fg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->fg_plan, n));
+        if (a->bg_plan) s = std::max(s, b200mrc_resample_workspace_bytes(a->bg_plan, n));
     }
-    L.scratch_bytes = s;
-    L.off_scratch = c.take<uint8_t>(s);
+    L.scratch_bytes = align_up(s, 256);
+    L.off_scratch = c.take<uint8_t>(L.scratch_bytes * L.gp.groups);
+    // ... and the optimise workspace (record plane + the sweep's mailbox), which no other stage writes
+    if (!mask_only) {
+        L.opt_bytes = align_up(optimise_workspace_bytes(W, H, n), 256);
+        L.off_opt = c.take<uint8_t>(L.opt_bytes * L.gp.groups);
+    }
     L.total = c.used();
     return L;
 }
@@ -120,6 +221,65 @@ int check_args(const b200mrc_decompose_args *a)
     return B200MRC_OK;
 }
 
+// Pages [p0, p0 + n) of the batch, every stage enqueued on `st`.
+int decompose_group(const b200mrc_decompose_args *a, const DecomposeLayout &L, int g, int p0, int n, cudaStream_t st)
+{
+    uint8_t *ws = (uint8_t *)a->workspace;
+    const int W = a->width, H = a->height, C = a->channels;
+    const uint8_t *img = a->img + (int64_t)p0 * a->img_page_stride;
+    uint8_t *mask = a->mask + (int64_t)p0 * a->mask_page_stride;
+    double *sigma = (double *)(ws + L.off_sigma) + p0;
+    uint8_t *gray = ws + L.off_gray + (size_t)p0 * L.gray_page;
+    void *scratch = ws + L.off_scratch + (size_t)g * L.scratch_bytes;
+    int rc;
+
+    // ---- noise estimate (or injected sigma)
+    const double *sigma_used = sigma;
+    if (a->flags & B200MRC_DECOMPOSE_NO_NOISE_EST) {
+        if (a->sigma_in) B200MRC_CUDA_TRY(cudaMemcpyAsync(sigma, a->sigma_in + p0, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        else sigma_used = nullptr;
+    } else {
+        rc = launch_estimate_noise(img, a->img_pitch, a->img_page_stride, C, W, H, n, sigma, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->sigma_out) {
+        if (sigma_used) B200MRC_CUDA_TRY(cudaMemcpyAsync(a->sigma_out + p0, sigma, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        else B200MRC_CUDA_TRY(cudaMemsetAsync(a->sigma_out + p0, 0, sizeof(double) * n, st));
+    }
+    // ---- gray (+ blur where sigma > 1) + Sauvola: mask = threshold_image(gray), or mask |= ... when the caller filled in
+    //      the hOCR line masks
+    rc = b200mrc_threshold_mask(img, a->img_pitch, a->img_page_stride, C, mask, a->mask_pitch, a->mask_page_stride, W, H, n,
+                                a->window, a->window, a->k, a->R, sigma_used,
+                                (a->flags & B200MRC_DECOMPOSE_OR_INTO_MASK) ? B200MRC_SAUVOLA_OR_INTO : 0,
+                                gray, L.gray_page * n + 256, st);
+    if (rc) return rc;
+    // ---- denoise
+    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) {
+        rc = launch_denoise(mask, a->mask_pitch, a->mask_page_stride, W, H, n, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) return B200MRC_OK;
+
+    // ---- fg / bg
+    uint8_t *fg_out = a->fg + (int64_t)p0 * a->fg_page_stride, *bg_out = a->bg + (int64_t)p0 * a->bg_page_stride;
+    uint8_t *fg_full = a->fg_plan ? ws + L.off_fgfull + (size_t)p0 * L.full_page : fg_out;
+    uint8_t *bg_full = a->bg_plan ? ws + L.off_bgfull + (size_t)p0 * L.full_page : bg_out;
+    const int64_t fgp = a->fg_plan ? (int64_t)L.full_pitch : a->fg_pitch, fgs = a->fg_plan ? (int64_t)L.full_page : a->fg_page_stride;
+    const int64_t bgp = a->bg_plan ? (int64_t)L.full_pitch : a->bg_pitch, bgs = a->bg_plan ? (int64_t)L.full_page : a->bg_page_stride;
+    rc = launch_optimise(mask, a->mask_pitch, a->mask_page_stride, img, a->img_pitch, a->img_page_stride, C,
+                         fg_full, fgp, fgs, 3, bg_full, bgp, bgs, 10, W, H, n, ws + L.off_opt + (size_t)g * L.opt_bytes, L.opt_bytes, st);
+    if (rc) return rc;
+    if (a->fg_plan) {
+        rc = b200mrc_resample(a->fg_plan, fg_full, fgp, fgs, fg_out, a->fg_pitch, a->fg_page_stride, n, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    if (a->bg_plan) {
+        rc = b200mrc_resample(a->bg_plan, bg_full, bgp, bgs, bg_out, a->bg_pitch, a->bg_page_stride, n, scratch, L.scratch_bytes, st);
+        if (rc) return rc;
+    }
+    return B200MRC_OK;
+}
+
 }  // namespace
 }  // namespace b200mrc
 
@@ -129,9 +289,10 @@ extern "C" int b200mrc_version(void) { return B200MRC_VERSION; }
 
 extern "C" int b200mrc_profile_enable(int on)
 {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
     return B200MRC_OK;
 }
 
@@ -140,6 +301,7 @@ extern "C" int b200mrc_profile_report(char *buf, size_t cap)
     // "kernel,launches,total_ms" lines; synchronises with every recorded event
     std::map<std::string, std::pair<int, double>> acc;
     std::vector<std::string> order;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &r : g_prof) {
         if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
         float ms = 0.f;
@@ -155,6 +317,23 @@ extern "C" int b200mrc_profile_report(char *buf, size_t cap)
     }
     if (buf && cap) { strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
     return (int)out.size();
+}
+
+extern "C" int b200mrc_set_tuning(const char *name, int value)
+{
+    if (!name) return B200MRC_ERR_INVALID;
+    std::call_once(g_tune_once, tune_init);
+    for (int i = 0; i < T_COUNT; i++)
+        if (!strcmp(name, k_tune_defs[i].name)) { g_tune[i].store(value); return B200MRC_OK; }
+    return B200MRC_ERR_INVALID;
+}
+
+extern "C" int b200mrc_get_tuning(const char *name, int *value)
+{
+    if (!name || !value) return B200MRC_ERR_INVALID;
+    for (int i = 0; i < T_COUNT; i++)
+        if (!strcmp(name, k_tune_defs[i].name)) { *value = tune((TuneKey)i); return B200MRC_OK; }
+    return B200MRC_ERR_INVALID;
 }
 
 extern "C" uint64_t b200mrc_launch_count(void) { return g_launch_count.load(); }
@@ -199,56 +378,24 @@ extern "C" int b200mrc_decompose(const b200mrc_decompose_args *a, void *stream)
     const DecomposeLayout L = decompose_layout(a);
     if (!a->workspace || a->workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    uint8_t *ws = (uint8_t *)a->workspace;
-    const int W = a->width, H = a->height, N = a->n_pages, C = a->channels;
-    double *sigma = (double *)(ws + L.off_sigma);
-    uint8_t *gray = ws + L.off_gray;
-    void *scratch = ws + L.off_scratch;
+    const int N = a->n_pages;
+    if (L.gp.streams == 0) return decompose_group(a, L, 0, 0, N, st);
 
-    // ---- noise estimate (or injected sigma)
-    const double *sigma_used = sigma;
-    if (a->flags & B200MRC_DECOMPOSE_NO_NOISE_EST) {
-        if (a->sigma_in) B200MRC_CUDA_TRY(cudaMemcpyAsync(sigma, a->sigma_in, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
-        else sigma_used = nullptr;
-    } else {
-        rc = launch_estimate_noise(a->img, a->img_pitch, a->img_page_stride, C, W, H, N, sigma, scratch, L.scratch_bytes, st);
-        if (rc) return rc;
+    // page groups round-robin over the internal streams; the caller's stream is the fork and the join point
+    DevStreams *ds = nullptr;
+    rc = internal_streams(&ds);
+    if (rc != B200MRC_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_streams_mu);        // one fork/join at a time per process: the events are shared
+    B200MRC_CUDA_TRY(cudaEventRecord(ds->ev_in, st));
+    for (int i = 0; i < L.gp.streams; i++) B200MRC_CUDA_TRY(cudaStreamWaitEvent(ds->s[i], ds->ev_in, 0));
+    int first_err = B200MRC_OK;
+    for (int g = 0; g < L.gp.groups && first_err == B200MRC_OK; g++) {
+        const int p0 = g * L.gp.per_group, n = std::min(L.gp.per_group, N - p0);
+        first_err = decompose_group(a, L, g, p0, n, ds->s[g % L.gp.streams]);
     }
-    if (a->sigma_out) {
-        if (sigma_used) B200MRC_CUDA_TRY(cudaMemcpyAsync(a->sigma_out, sigma, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
-        else B200MRC_CUDA_TRY(cudaMemsetAsync(a->sigma_out, 0, sizeof(double) * N, st));
+    for (int i = 0; i < L.gp.streams; i++) {             // join even after an error: nothing may run past the caller's next op
+        cudaEventRecord(ds->ev_done[i], ds->s[i]);
+        cudaStreamWaitEvent(st, ds->ev_done[i], 0);
     }
-    // ---- gray (+ blur where sigma > 1)
-    rc = launch_gray_blur(a->img, a->img_pitch, a->img_page_stride, C, gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page,
-                          W, H, N, sigma_used, nullptr, st);
-    if (rc) return rc;
-    // ---- Sauvola: mask = threshold_image(gray), or mask |= ... when the caller filled in the hOCR line masks
-    rc = b200mrc_sauvola(gray, (int64_t)L.gray_pitch, (int64_t)L.gray_page, a->mask, a->mask_pitch, a->mask_page_stride,
-                         W, H, N, a->window, a->window, a->k, a->R,
-                         (a->flags & B200MRC_DECOMPOSE_OR_INTO_MASK) ? B200MRC_SAUVOLA_OR_INTO : 0, st);
-    if (rc) return rc;
-    // ---- denoise
-    if (a->flags & B200MRC_DECOMPOSE_DENOISE_FAST) {
-        rc = launch_denoise(a->mask, a->mask_pitch, a->mask_page_stride, W, H, N, scratch, L.scratch_bytes, st);
-        if (rc) return rc;
-    }
-    if (a->flags & B200MRC_DECOMPOSE_MASK_ONLY) return B200MRC_OK;
-
-    // ---- fg / bg
-    uint8_t *fg_full = a->fg_plan ? ws + L.off_fgfull : a->fg;
-    uint8_t *bg_full = a->bg_plan ? ws + L.off_bgfull : a->bg;
-    const int64_t fgp = a->fg_plan ? (int64_t)L.full_pitch : a->fg_pitch, fgs = a->fg_plan ? (int64_t)L.full_page : a->fg_page_stride;
-    const int64_t bgp = a->bg_plan ? (int64_t)L.full_pitch : a->bg_pitch, bgs = a->bg_plan ? (int64_t)L.full_page : a->bg_page_stride;
-    rc = launch_optimise(a->mask, a->mask_pitch, a->mask_page_stride, a->img, a->img_pitch, a->img_page_stride, C,
-                         fg_full, fgp, fgs, 3, bg_full, bgp, bgs, 10, W, H, N, scratch, L.scratch_bytes, st);
-    if (rc) return rc;
-    if (a->fg_plan) {
-        rc = b200mrc_resample(a->fg_plan, fg_full, fgp, fgs, a->fg, a->fg_pitch, a->fg_page_stride, N, scratch, L.scratch_bytes, st);
-        if (rc) return rc;
-    }
-    if (a->bg_plan) {
-        rc = b200mrc_resample(a->bg_plan, bg_full, bgp, bgs, a->bg, a->bg_pitch, a->bg_page_stride, N, scratch, L.scratch_bytes, st);
-        if (rc) return rc;
-    }
-    return B200MRC_OK;
+    return first_err;
 }

@@ -30,13 +30,37 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
 
 // Optional per-kernel CUDA-event timing (b200mrc_profile_enable / b200mrc_profile_report): an event
 // pair is recorded on the launching stream around every kernel while profiling is on.
-void prof_begin(const char *kernel, cudaStream_t st);
-void prof_end(cudaStream_t st);
+int prof_begin(const char *kernel, cudaStream_t st);      // -> record index, -1 when profiling is off
+void prof_end(int record, cudaStream_t st);
 struct ProfScope {
-    cudaStream_t st;
-    ProfScope(const char *kernel, cudaStream_t s) : st(s) { prof_begin(kernel, s); }
-    ~ProfScope() { prof_end(st); }
+    cudaStream_t st; int rec;
+    ProfScope(const char *kernel, cudaStream_t s) : st(s), rec(prof_begin(kernel, s)) {}
+    ~ProfScope() { prof_end(rec, st); }
 };
+
+// Tuning knobs (A/B runs, tests).  Each is initialised ONCE per process from the environment variable B200MRC_<NAME>
+// and can be changed at run time with b200mrc_set_tuning(); launchers read them as relaxed atomics -- no getenv() on a
+// launch path.  INTEGRATION.md lists them.
+enum TuneKey {
+    T_IIRW_MODE,        // sweep form: 0 auto (by batch size), 1 single (one warp per strip), 2 trio      env: single | trio
+    T_IIRW_TPC,         // trio form: strips per CTA (1..3)
+    T_IIRW_FEED,        // single form input feed: 0 auto, 1 tma, 2 async                                  env: tma | async
+    T_IIRW_PSLEEP,      // trio form: producer back-off in ns
+    T_IIRW_WPC,         // single form: warps per CTA
+    T_FIRW_BAND,        // FIR pass: rows per band
+    T_FIRW_WPC,         // FIR pass: warps per CTA
+    T_FUSED_NT,         // fused threshold: threads per CTA (0 auto, 128 | 192 | 256)
+    T_FUSED_BANDS,      // fused threshold: row bands per strip (0 auto)
+    T_THRESHOLD_PATH,   // 0 fused, 1 legacy (gray_blur + sauvola kernels)                                 env: legacy
+    T_OPT_PATH,         // 0 split (FIR + sweep), 1 generic fused sweep                                    env: generic
+    T_NOISE_DIRECT,     // 1: one-thread-per-coefficient wavelet kernel
+    T_RESAMPLE_2PASS,   // 1: separate horizontal / vertical resample kernels
+    T_TILE_H,           // tile resampler: output rows per CTA (16 | 32 | 64)
+    T_DECOMPOSE_GROUPS, // page groups per b200mrc_decompose call (0 auto)
+    T_DECOMPOSE_STREAMS,// internal streams the groups run on (0 auto)
+    T_COUNT
+};
+int tune(TuneKey k);
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -12,6 +12,7 @@
 // per-page decision (blur or plain gray copy, and the radius) is taken by the kernel without a
 // host round trip; two tile configurations cover radius 0..16 and 17..128.
 #include "common.cuh"
+#include "blur.cuh"
 #include <cstdlib>
 
 namespace b200mrc {
@@ -26,38 +27,11 @@ struct GrayBlurParams {
     int rlo;                 // tiled kernel: smallest radius it handles (5 when the fast kernel ran, else 0)
 };
 
-__device__ __forceinline__ int reflect_idx(int i, int n)
-{
-    if (n == 1) return 0;
-    const int per = 2 * n;
-    i %= per; if (i < 0) i += per;
-    return i < n ? i : per - 1 - i;
-}
-
 __device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch, int C, int y, int x)
 {
     const uint8_t *px = page + (int64_t)y * pitch + (int64_t)x * C;
     if (C == 1) return px[0];
     return luma_l24(px[0], px[1], px[2]);
-}
-
-// numpy pairwise sum (n <= 128 path): what phi_x.sum() does in scipy's _gaussian_kernel1d
-__device__ double np_sum(const double *a, int n)
-{
-    if (n < 8) {
-        double res = 0.0;
-        for (int i = 0; i < n; i++) res = __dadd_rn(res, a[i]);
-        return res;
-    }
-    double r[8];
-    for (int j = 0; j < 8; j++) r[j] = a[j];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8)
-        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; i++) res = __dadd_rn(res, a[i]);
-    return res;
 }
 
 // One tile of one page.  256 threads as 32 x 8: no integer division in the loops.
@@ -105,29 +79,12 @@ __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t
 
 __device__ __forceinline__ int page_radius(const GrayBlurParams &p, int page, double &sigma)
 {
-    const double sig_est = p.sigma ? p.sigma[page] : 0.0;
-    sigma = 0.0;
-    if (!(sig_est > 1.0)) return 0;            // NaN compares false: no blur
-    sigma = sig_est * 0.1;
-    const double rr = 4.0 * sigma + 0.5;
-    return rr > 1.0e6 ? 1000000 : (int)rr;
+    return blur_radius_of(p.sigma, page, sigma);
 }
 
 __device__ __forceinline__ void blur_weights(int radius, double sigma, double *sw, double *sphi)
 {
-    // weights (scipy _gaussian_kernel1d), double; thread-serial sum so the summation order is fixed
-    const int tid = threadIdx.x;
-    for (int i = tid; i <= 2 * radius; i += 256) {
-        const int j = i - radius;
-        const double sigma2 = sigma * sigma;
-        sphi[i] = exp(__dmul_rn(-0.5 / sigma2, (double)(j * j)));
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const double sum = np_sum(sphi, 2 * radius + 1);
-        for (int j = 0; j <= radius; j++) sw[j] = sphi[radius + j] / sum;
-    }
-    __syncthreads();
+    blur_weights_cta(radius, sigma, sw, sphi);
 }
 
 // Small-radius configuration (0..RHI): one CTA per tile, grid over (tiles, pages).
@@ -224,9 +181,6 @@ __device__ __forceinline__ uint32_t load_gray4(const GrayBlurParams &p, const ui
     for (int k = 0; k < 4; k++) r |= load_gray(in, p.in_pitch, C, y, reflect_idx(x + k, p.W)) << (8 * k);
     return r;
 }
-
-// (double)x for 0 <= x < 2^31 without the conversion unit: 2^52 + x is exact, subtract 2^52 on the FP64 pipe
-__device__ __forceinline__ double u2d(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
 
 template <int R, int C>
 __device__ __forceinline__ void blur_march(const GrayBlurParams &p, const uint8_t *in, uint8_t *out,
@@ -326,13 +280,10 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
                          !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
     if (fast_ok) {
         dim3 grid(cdiv(W, 120), cdiv(cdiv(H, FB_BAND), 8), N);
-        const char *mb = getenv("B200MRC_BLUR_MINB");
-        const int minb = mb ? atoi(mb) : 6;        // 6 CTAs / SM (40 registers, a few spills) beats 4 (60 registers) by 10 %
+        // 6 CTAs / SM (40 registers, a few spills) beats 4 (60 registers) by 10 %
         { ProfScope _ps("k_gray_blur_fast", st);
           if (C == 1) k_gray_blur_fast<1, 4><<<grid, 256, 0, st>>>(p);
-          else if (minb == 5) k_gray_blur_fast<3, 5><<<grid, 256, 0, st>>>(p);
-          else if (minb == 6) k_gray_blur_fast<3, 6><<<grid, 256, 0, st>>>(p);
-          else k_gray_blur_fast<3, 4><<<grid, 256, 0, st>>>(p); }
+          else k_gray_blur_fast<3, 6><<<grid, 256, 0, st>>>(p); }
         B200MRC_LAUNCH_CHECK();
         p.rlo = 5;
     }
@@ -356,6 +307,38 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
         B200MRC_LAUNCH_CHECK();
     }
     if (sigma) {
+        constexpr int TH = 16, TW = 32, RHI = 128;
+        constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<17, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = cdiv(W, TW) * cdiv(H, TH);
+        int grid = dev_info().sm_count * 2;
+        if (grid > tiles) grid = tiles;
+        { ProfScope _ps("k_gray_blur_large<17..128>", st); k_gray_blur_large<17, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
+        B200MRC_LAUNCH_CHECK();
+    }
+    return B200MRC_OK;
+}
+
+// Only the pages whose blur radius is >= rmin (3 <= rmin <= 5), through the tiled persistent kernels: every other page is
+// skipped on the device.  Used by the fused threshold path (sauvola_fused.cu), which blurs radius <= 2 itself.
+int launch_gray_blur_min_radius(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C,
+                                uint8_t *out, int64_t out_pitch, int64_t out_stride,
+                                int W, int H, int N, const double *sigma, int rmin, int *err_flag, cudaStream_t st)
+{
+    if (!sigma) return B200MRC_OK;
+    if (rmin != 3) return B200MRC_ERR_UNSUPPORTED;
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0};
+    {
+        constexpr int TH = 32, TW = 128, RHI = 16;
+        constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<3, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = cdiv(W, TW) * cdiv(H, TH);
+        int grid = dev_info().sm_count * 4;
+        if (grid > tiles) grid = tiles;
+        { ProfScope _ps("k_gray_blur_large<3..16>", st); k_gray_blur_large<3, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
+        B200MRC_LAUNCH_CHECK();
+    }
+    {
         constexpr int TH = 16, TW = 32, RHI = 128;
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
         B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<17, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

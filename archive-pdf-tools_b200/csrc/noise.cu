@@ -295,7 +295,7 @@ int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride
     p.oh = (p.he - p.hs + 3) / 2; p.ow = (p.we - p.ws + 3) / 2;
     p.keys = (uint32_t *)workspace;
     p.sigma_out = sigma_out;
-    if (getenv("B200MRC_NOISE_DIRECT")) {
+    if (tune(T_NOISE_DIRECT)) {                              // A/B switch
         dim3 grid(cdiv(p.ow, 32), cdiv(p.oh, 8), N);
         { ProfScope _ps("k_noise_dd", st); k_noise_dd<<<grid, 256, 0, st>>>(p); }
     } else {

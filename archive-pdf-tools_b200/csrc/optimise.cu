@@ -315,8 +315,8 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     const OptLayout L = opt_layout(W, H, N);
     if (!workspace || workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
     uint8_t *ws = (uint8_t *)workspace;
-    const char *path = getenv("B200MRC_OPT_PATH");          // "split" (default) | "generic": A/B switch for profiling
-    if (nfg == 3 && nbg == 10 && (!path || !strcmp(path, "split"))) {
+    // tuning key OPT_PATH: split (default) | generic, A/B switch for profiling
+    if (nfg == 3 && nbg == 10 && tune(T_OPT_PATH) == 0) {
         // production path: parallel FIR record plane + row-sequential warp-strip sweep (optimise_split.cu)
         const int frc = launch_optimise_split(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
                                               obg, bpitch, bstride, W, H, N, ws + L.off_rec, (uint32_t *)(ws + L.off_mailbox),

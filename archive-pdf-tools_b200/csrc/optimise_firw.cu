@@ -18,6 +18,9 @@
 //     enters / leaves a box as one multiply-add per word with its 0/1 layer flag;
 //   * the 6-column fg window and the two 10-column halves of the bg window are sums of warp shuffles;
 //     the bg window is evaluated only in rows where the strip holds a mask pixel.
+// The kernel also clears the sweep's mailbox rows (128 B per strip row, one coalesced store per warp and row): the sweep
+// validates a hand-off word by its launch tag, so the rows must not hold another stage's bytes that happen to carry the
+// tag -- the workspace is shared with other stages and with earlier launches.  Clearing here costs no extra pass.
 #include "common.cuh"
 
 namespace b200mrc {
@@ -35,6 +38,7 @@ struct FirWParams {
     uint8_t *rec; int64_t rpitch, rstride;
     int W, H, N, S, n_bands, band_h;
     int64_t jobs;
+    uint32_t *mailbox; int S_sweep;      // the sweep's hand-off rows [N][S_sweep][H][32], cleared here (see below)
 };
 
 template <int C> struct FirSmem {
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
     const uint8_t *mp = p.mask + (int64_t)page * p.mstride + colc;
     uint8_t *rp = p.rec + (int64_t)page * p.rstride + colc * 8;
     uint8_t *myslot = stage + lane * SM::slot;
+    uint32_t *mbz = (p.mailbox && strip < p.S_sweep)
+                        ? p.mailbox + (((int64_t)page * p.S_sweep + strip) * H + by0) * 32 + lane : nullptr;
 
     // lanes outside the page never copy: their slots stay zero (mask 0, pixels 0) and vw clears the flags
     for (int s = 0; s < DEPTH; s++) {
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
                     }
                 }
             }
+            if (mbz) { *mbz = 0u; mbz += 32; }
             if (real) {
                 uint4 *dst = reinterpret_cast<uint4 *>(rp + (int64_t)y * p.rpitch);
                 dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(128) k_opt_fir_w(const FirWParams p)
 int launch_opt_fir_warp(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                         const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                         uint8_t *rec, int64_t rpitch, int64_t rstride,
-                        int W, int H, int N, int band_h, int wpc, cudaStream_t st)
+                        int W, int H, int N, int band_h, int wpc, uint32_t *mailbox, int S_sweep, cudaStream_t st)
 {
     if (wpc < 1 || wpc > 4 || band_h < 1) return B200MRC_ERR_UNSUPPORTED;
     if (rpitch < (int64_t)((W + 3) / 4 * 4) * 8) return B200MRC_ERR_INVALID;
@@ -307,6 +314,7 @@ int launch_opt_fir_warp(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     p.rec = rec; p.rpitch = rpitch; p.rstride = rstride;
     p.W = W; p.H = H; p.N = N; p.S = cdiv(W, RW); p.band_h = band_h; p.n_bands = cdiv(H, band_h);
     p.jobs = (int64_t)N * p.S * p.n_bands;
+    p.mailbox = mailbox; p.S_sweep = S_sweep;
     const size_t smem = (size_t)wpc * (C == 3 ? FirSmem<3>::warp_bytes : FirSmem<1>::warp_bytes);
     const void *kern = C == 3 ? (const void *)k_opt_fir_w<3> : (const void *)k_opt_fir_w<1>;
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -21,7 +21,7 @@ namespace b200mrc {
 int launch_opt_fir_warp(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                         const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                         uint8_t *rec, int64_t rpitch, int64_t rstride,
-                        int W, int H, int N, int band_h, int wpc, cudaStream_t st);
+                        int W, int H, int N, int band_h, int wpc, uint32_t *mailbox, int S_sweep, cudaStream_t st);
 int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                         const uint8_t *rec, int64_t rpitch, int64_t rstride,
                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
@@ -47,12 +47,13 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
     if (mpitch < need_m || ipitch < need_i || fpitch < need_i || bpitch < need_i) return B200MRC_ERR_UNSUPPORTED;
     if (N > 65535) return B200MRC_ERR_UNSUPPORTED;
     const int64_t rpitch = optimise_split_rec_pitch(W), rstride = rpitch * H;
-    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    const int firw_band = tune(T_FIRW_BAND), firw_wpc = tune(T_FIRW_WPC), iirw_wpc = tune(T_IIRW_WPC);
+    // the FIR pass also clears the sweep's mailbox rows (128 columns per sweep strip)
     int rc = launch_opt_fir_warp(mask, mpitch, mstride, img, ipitch, istride, C, rec, rpitch, rstride, W, H, N,
-                                 env_int("B200MRC_FIRW_BAND", 256), env_int("B200MRC_FIRW_WPC", 4), st);
+                                 firw_band, firw_wpc, mailbox, cdiv(W, 128), st);
     if (rc != B200MRC_OK) return rc;
     return launch_opt_iir_warp(img, ipitch, istride, C, rec, rpitch, rstride, ofg, fpitch, fstride, obg, bpitch, bstride,
-                               W, H, N, mailbox, ticket, env_int("B200MRC_IIRW_WPC", 2), st);
+                               W, H, N, mailbox, ticket, iirw_wpc, st);
 }
 
 }  // namespace b200mrc

@@ -31,8 +31,8 @@
 #include "tma.cuh"
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
+#include <algorithm>
+#include <atomic>
 
 namespace b200mrc {
 namespace {
@@ -807,12 +807,10 @@ size_t iirw3_smem_bytes(int C, int tpc) { return MTAB_BYTES + (size_t)tpc * (C =
 size_t iirw_mailbox_words(int W, int H, int N) { return (size_t)N * cdiv(W, SWW) * (size_t)H * MBW; }
 
 namespace {
-// Launch epochs: mailbox words written by launch e carry tag(e); a mailbox region is cleared whenever it is
-// first used, used with another geometry, or the 8-bit epoch wraps, so a stale word can never match.
-struct MbState { int W, H, N, C; };
-std::mutex g_mb_mutex;
-std::map<const void *, MbState> g_mb_state;
-unsigned g_epoch = 0;
+// Launch epochs: mailbox words written by launch e carry tag(e) (1..255).  k_opt_fir_w clears every mailbox row of the
+// batch right before the sweep (optimise_firw.cu), so a word is either zero (tag 0: poll again) or written by this launch;
+// the epoch only guards against a caller who skips the FIR pass.
+std::atomic<unsigned> g_epoch{0};
 }  // namespace
 
 // The record plane `rec` must hold k_opt_fir's fmt-1 records.  ticket: 1 word.
@@ -823,26 +821,17 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
                         int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, cudaStream_t st)
 {
     if (wpc < 1 || wpc > 8) return B200MRC_ERR_UNSUPPORTED;
-    unsigned epoch;
-    {
-        std::lock_guard<std::mutex> lk(g_mb_mutex);
-        g_epoch = g_epoch % 255u + 1u;                       // 1..255
-        if (g_epoch == 1u) g_mb_state.clear();               // wrapped: every region is cleared before its next use
-        auto it = g_mb_state.find(mailbox);
-        const bool same = it != g_mb_state.end() && it->second.W == W && it->second.H == H && it->second.N == N && it->second.C == C;
-        if (!same) {
-            B200MRC_CUDA_TRY(cudaMemsetAsync(mailbox, 0, iirw_mailbox_words(W, H, N) * sizeof(uint32_t), st));
-            g_mb_state[mailbox] = MbState{W, H, N, C};
-        }
-        epoch = g_epoch;
-    }
+    const unsigned epoch = g_epoch.fetch_add(1u) % 255u + 1u;    // 1..255
+    struct { unsigned psleep; int mode, tpc, feed; } env;
+    env.psleep = (unsigned)tune(T_IIRW_PSLEEP); env.mode = tune(T_IIRW_MODE); env.feed = tune(T_IIRW_FEED);
+    env.tpc = std::min(3, std::max(1, tune(T_IIRW_TPC)));
     IirWParams p;
     p.img = img; p.ipitch = ipitch; p.istride = istride; p.rec = rec; p.rpitch = rpitch; p.rstride = rstride;
     p.ofg = ofg; p.fpitch = fpitch; p.fstride = fstride; p.obg = obg; p.bpitch = bpitch; p.bstride = bstride;
     p.W = W; p.H = H; p.N = N; p.S = cdiv(W, SWW);
     p.mailbox = mailbox; p.ticket = ticket;
     p.tag = ((epoch & 0xfu) << 12) | ((epoch >> 4) << 28);
-    { const char *e = getenv("B200MRC_IIRW_PSLEEP"); p.psleep = e ? (unsigned)atoi(e) : 300u; }
+    p.psleep = env.psleep;
     const int jobs = N * p.S;
     B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
     // Which form (measured on B200, 3300x2550 RGB pages, ms per launch; profiles/r1q_ab_sweep.txt):
@@ -852,14 +841,10 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     // The trio form (one warp per layer + a producer thread, shared TMA-fed stages) wins while the machine is not full;
     // from ~6 strips per SM on the one-warp form is as fast and leaves more room for concurrent kernels.
     // B200MRC_IIRW_MODE=trio|single and B200MRC_IIRW_FEED=tma|async (single form) override for A/B runs and tests.
-    const char *mode = getenv("B200MRC_IIRW_MODE");
     const bool big = jobs >= 6 * dev_info().sm_count;
-    const bool use_trio = mode ? strcmp(mode, "single") != 0 : !big;
+    const bool use_trio = env.mode ? env.mode == 2 : !big;
     if (use_trio) {
-        const char *e = getenv("B200MRC_IIRW_TPC");
-        int tpc = e ? atoi(e) : 2;
-        if (tpc < 1) tpc = 1;
-        if (tpc > 3) tpc = 3;
+        const int tpc = env.tpc;
         const size_t smem3 = iirw3_smem_bytes(C, tpc);
         if (smem3 > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
         const void *kern = tpc == 1 ? (C == 3 ? (const void *)k_opt_iir_w3<3, IST, 1> : (const void *)k_opt_iir_w3<1, IST, 1>)
@@ -873,8 +858,7 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     }
     const size_t smem = iirw_smem_bytes(C, wpc);
     if (smem > (size_t)dev_info().max_smem_optin) return B200MRC_ERR_UNSUPPORTED;
-    const char *feed = getenv("B200MRC_IIRW_FEED");
-    const bool use_tma = feed ? !strcmp(feed, "tma") : big;
+    const bool use_tma = env.feed ? env.feed == 1 : big;
     const void *kern = use_tma ? (C == 3 ? (const void *)k_opt_iir_w<3, false> : (const void *)k_opt_iir_w<1, false>)
                                : (C == 3 ? (const void *)k_opt_iir_w<3, true> : (const void *)k_opt_iir_w<1, true>);
     B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -490,15 +490,14 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
         return B200MRC_OK;
     }
     if (pl->tile_F == 3 && pl->tile_T == 12 && !(src_pitch & 3) && !(src_stride & 3) && !((uintptr_t)src & 3) &&
-        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, 16) <= 65535 && !getenv("B200MRC_RESAMPLE_2PASS")) {
+        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, 16) <= 65535 && !tune(T_RESAMPLE_2PASS)) {
         TileParams t;
         t.in = src; t.in_pitch = src_pitch; t.in_stride = src_stride; t.out = out; t.out_pitch = out_pitch; t.out_stride = out_page_stride;
         t.in_w = pl->SW; t.in_h = pl->SH; t.out_w = pl->OW; t.out_h = pl->OH; t.ksize_h = pl->ksize_h; t.ksize_v = pl->ksize_v;
         t.bounds_h = pl->d_bounds_h; t.kk_h = pl->d_kk_h; t.bounds_v = pl->d_bounds_v; t.kk_v = pl->d_kk_v;
         t.offx = pl->offx; t.offy = pl->offy; t.ux0 = pl->ux0; t.ux1 = pl->ux1; t.uy0 = pl->uy0; t.uy1 = pl->uy1;
         memcpy(t.kh, pl->kh, sizeof(t.kh)); memcpy(t.kv, pl->kv, sizeof(t.kv));
-        const char *the = getenv("B200MRC_TILE_H");
-        const int toh = the ? atoi(the) : 32;
+        const int toh = tune(T_TILE_H);
         dim3 grid(cdiv(pl->OW, TOW), cdiv(pl->OH, toh == 64 ? 64 : (toh == 16 ? 16 : 32)), n_pages);
         { ProfScope _ps("k_resample_tile", st);
           if (pl->C == 1) {

@@ -1,4 +1,5 @@
-// sauvola.cu -- k_sauvola_mask: Sauvola local-adaptive threshold (reference: binarise_sauvola,
+// sauvola.cu -- k_sauvola_mask_w: Sauvola local-adaptive threshold on a gray plane, any 4-byte aligned rows (the general
+// form: small crops, k < 0, inverted input; 16-byte aligned planes take the fused kernel of sauvola_fused.cu).  Sauvola local-adaptive threshold (reference: binarise_sauvola,
 // cython/sauvola.pyx:29-222, called through threshold_image, internetarchivepdf/mrc.py:58-87).
 //
 // Semantics (closed form of the reference's running sums, see oracle/mrc_oracle.c orc_sauvola):
@@ -14,9 +15,8 @@
 //     entering row and subtracts the leaving row (32-bit vector loads, L2-resident re-reads);
 //   * the horizontal window sum is a difference of two entries of the per-row prefix of the
 //     column sums: thread-local prefix -> warp-shuffle inclusive scan; prefixes are published in a
-//     bank-conflict-free SoA layout (column c -> [c&3][c>>2]).  Production form (k_sauvola_mask_w):
-//     the published prefixes are warp-local and a pixel adds the totals of the warps between its two
-//     entries -> one CTA barrier per row.  A/B form (k_sauvola_mask): CTA-wide prefixes, two barriers;
+//     bank-conflict-free SoA layout (column c -> [c&3][c>>2]); the published prefixes are warp-local and a
+//     pixel adds the totals of the warps between its two entries -> one CTA barrier per row;
 //   * uint32 wrap-around arithmetic is exact because every window sum is < 2^32 for w <= 255;
 //   * S/n and Q/n are exact floors computed on the FP64 pipe (floor((a+0.5)*(1/n))); the test runs in
 //     FP64 with __dmul_rn/__dadd_rn so nvcc cannot contract to FMA.
@@ -53,204 +53,8 @@ __device__ __forceinline__ uint32_t load_word_clamped(const uint8_t *row, int gx
     return w;
 }
 
-template <bool KNEG, int MINB>
-__global__ void __launch_bounds__(ST, MINB) k_sauvola_mask(const SauvolaParams p)
-{
-    // prefix of column sums for the current row, SoA layout, double buffered
-    __shared__ uint2 sP[2][SK * (ST + 1)];
-    __shared__ uint2 sWT[2][ST / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
-    const int page = blockIdx.y;
-    const int sx0 = strip * p.strip_w;
-    const int ex0 = sx0 - p.ext_left;             // first input column of this CTA (multiple of 4)
-    const int by0 = band * p.band_h;
-    const int by1 = min(p.H, by0 + p.band_h);
-    const int W = p.W, H = p.H;
-    const uint8_t *in = p.in + (int64_t)page * p.in_stride;
-    uint8_t *out = p.out + (int64_t)page * p.out_stride;
-
-    const int i0 = tid * SK;                      // local column of this thread's first pixel
-    const int gx = ex0 + i0;                      // global column (multiple of 4, may be < 0 or >= W)
-    const bool is_out = (gx >= sx0) && (gx < sx0 + p.strip_w) && (gx < W);
-
-    const uint32_t inv = (p.flags & B200MRC_SAUVOLA_INVERT_INPUT) ? 0xffffffffu : 0u;   // threshold 255 - p (mrc.py:226)
-    uint32_t cs[SK], cq[SK];
-#pragma unroll
-    for (int j = 0; j < SK; j++) { cs[j] = 0; cq[j] = 0; }
-    // row-invariant per-thread constants: smem slots of the two prefix entries of each pixel's window,
-    // the window width, and where this thread publishes its own prefixes
-    int slot_hi[SK], slot_lo[SK], slot_st[SK], nxv[SK];
-#pragma unroll
-    for (int j = 0; j < SK; j++) {
-        const int x = gx + j, i = i0 + j;
-        const int chi = i + p.r + 1, clo = max(i - p.l + 1, 0), cst = i + 1;
-        slot_hi[j] = (chi & 3) * (ST + 1) + (chi >> 2);
-        slot_lo[j] = (clo & 3) * (ST + 1) + (clo >> 2);
-        slot_st[j] = (cst & 3) * (ST + 1) + (cst >> 2);
-        nxv[j] = (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0;
-    }
-    const bool nx_uniform = nxv[0] == nxv[1] && nxv[1] == nxv[2] && nxv[2] == nxv[3];
-
-    // ---- band warm-up: column sums over the window rows of the first output row
-    {
-        const int r0 = max(0, by0 - p.o + 1), r1 = min(H - 1, by0 + p.u);
-        for (int yy = r0; yy <= r1; yy++) {
-            uint32_t w = load_word_clamped(in + (int64_t)yy * p.in_pitch, gx, W, inv);
-#pragma unroll
-            for (int j = 0; j < SK; j++) {
-                uint32_t v = (w >> (8 * j)) & 0xFFu;
-                cs[j] += v; cq[j] += v * v;
-            }
-        }
-    }
-    if (tid == 0) {
-#pragma unroll
-        for (int b = 0; b < 2; b++)
-            for (int j = 0; j < SK; j++) sP[b][j * (ST + 1)] = make_uint2(0u, 0u);   // never used: c=0 slot set below
-    }
-
-    // loads run two rows ahead of their use (L2/HBM latency >> one row step): stage A feeds the
-    // next iteration, stage B the one after.  Words are loaded raw through three running row pointers
-    // and masked (columns outside the page read as 0) only when they are consumed, so nothing waits
-    // on a load in the iteration that issues it.
-    const bool lok = gx >= 0 && gx < W;
-    const uint32_t lmask = !lok ? 0u : (W - gx >= 4 ? 0xffffffffu : (1u << (8 * (W - gx))) - 1u);
-    const uint8_t *pe = in + (int64_t)(by0 + 1 + p.u) * p.in_pitch + gx;      // entering row of the next load_upd
-    const uint8_t *pl = in + (int64_t)(by0 + 1 - p.o) * p.in_pitch + gx;      // leaving row
-    const uint8_t *pc = in + (int64_t)(by0 + 1) * p.in_pitch + gx;            // its own pixels
-    auto load_upd = [&](int yu, uint32_t &we, uint32_t &wl, uint32_t &wc) {
-        // words needed to move the window from row yu-1 to row yu, and row yu's own pixels
-        we = 0; wl = 0; wc = 0;
-        if (yu < by1 && lok) {
-            if (yu + p.u < H) we = __ldg(reinterpret_cast<const uint32_t *>(pe));
-            if (yu - p.o >= 0) wl = __ldg(reinterpret_cast<const uint32_t *>(pl));
-            wc = __ldg(reinterpret_cast<const uint32_t *>(pc));
-        }
-        pe += p.in_pitch; pl += p.in_pitch; pc += p.in_pitch;
-    };
-    uint32_t wcur = load_word_clamped(in + (int64_t)by0 * p.in_pitch, gx, W, inv);
-    uint32_t weA, wlA, wcA, weB, wlB, wcB;
-    load_upd(by0 + 1, weA, wlA, wcA);
-    load_upd(by0 + 2, weB, wlB, wcB);
-    int ny_cached = -1;
-    double rn_u = 0.0;
-
-    for (int y = by0; y < by1; y++) {
-        const int buf = (y - by0) & 1;
-        // rows outside the page were not loaded (0) and must stay 0 under inversion
-        const uint32_t inv_e = (y + 1 + p.u < H && y + 1 < by1) ? inv : 0u, inv_l = (y + 1 - p.o >= 0 && y + 1 < by1) ? inv : 0u,
-                       inv_c = (y + 1 < by1) ? inv : 0u;
-        const uint32_t wenter = (weA ^ inv_e) & lmask, wleave = (wlA ^ inv_l) & lmask, wnext = (wcA ^ inv_c) & lmask;
-        weA = weB; wlA = wlB; wcA = wcB;
-        load_upd(y + 3, weB, wlB, wcB);
-
-        // ---- prefix of the column sums across the CTA
-        uint32_t ps[SK], pq[SK];
-        ps[0] = cs[0]; pq[0] = cq[0];
-#pragma unroll
-        for (int j = 1; j < SK; j++) { ps[j] = ps[j - 1] + cs[j]; pq[j] = pq[j - 1] + cq[j]; }
-        uint32_t ws = ps[SK - 1], wq = pq[SK - 1];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t ts = __shfl_up_sync(0xffffffffu, ws, d);
-            uint32_t tq = __shfl_up_sync(0xffffffffu, wq, d);
-            if (lane >= d) { ws += ts; wq += tq; }
-        }
-        if (lane == 31) sWT[buf][warp] = make_uint2(ws, wq);
-        __syncthreads();
-        uint32_t bs = ws - ps[SK - 1], bq = wq - pq[SK - 1];     // exclusive within the warp
-#pragma unroll
-        for (int w2 = 0; w2 < ST / 32; w2++) {
-            uint2 t = sWT[buf][w2];
-            if (w2 < warp) { bs += t.x; bq += t.y; }
-        }
-        // inclusive prefix up to local column c-1 is stored at "c": column c -> [c&3][c>>2]
-#pragma unroll
-        for (int j = 0; j < SK; j++) sP[buf][slot_st[j]] = make_uint2(bs + ps[j], bq + pq[j]);
-        if (tid == 0) sP[buf][0] = make_uint2(0u, 0u);            // c = 0: empty prefix
-        __syncthreads();
-
-        // ---- per-pixel test
-        if (is_out) {
-            const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
-            uint32_t bits = 0;
-            // S/n and Q/n on the (otherwise idle) FP64 pipe: floor((a + 0.5) * (1/n)) == a / n exactly,
-            // because (a + 0.5)/n is at least 1/(2n) away from every integer while the double product is
-            // accurate to 2^-52 relative (a < 2^32, n <= 65025).  The quotients come out as the doubles
-            // the test needs, so no int->double conversions of m and v remain.
-            if (nx_uniform && ny != ny_cached) { rn_u = 1.0 / (double)(nxv[0] * ny); ny_cached = ny; }
-            if (nx_uniform) {
-                // interior thread: one window area for its 4 pixels (n > 0 because the thread is inside the page)
-#pragma unroll
-                for (int j = 0; j < SK; j++) {
-                    const uint2 hi = sP[buf][slot_hi[j]];
-                    const uint2 lo = sP[buf][slot_lo[j]];
-                    const double md = floor(__dmul_rn(__dadd_rn((double)(hi.x - lo.x), 0.5), rn_u));   // (double)(S / n)
-                    const double qd = floor(__dmul_rn(__dadd_rn((double)(hi.y - lo.y), 0.5), rn_u));   // (double)(Q / n)
-                    const double mm = __dmul_rn(md, md);                                                // exact (integers < 2^53)
-                    const double v = __dadd_rn(qd, -mm);
-                    const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
-                    const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
-                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
-                    const double lhs = __dmul_rn(t, t);
-                    const bool fg = KNEG ? ((t <= 0.0) && (lhs >= rhs)) : ((t <= 0.0) || (lhs <= rhs));
-                    bits |= (fg ? 1u : 0u) << (8 * j);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < SK; j++) {
-                    const uint2 hi = sP[buf][slot_hi[j]];
-                    const uint2 lo = sP[buf][slot_lo[j]];
-                    const uint32_t S = hi.x - lo.x, Q = hi.y - lo.y;
-                    const int n = nxv[j] * ny;
-                    uint32_t fg = 0;
-                    if (n > 0) {
-                        const double rn = 1.0 / (double)n;
-                        const double md = floor(__dmul_rn(__dadd_rn((double)S, 0.5), rn));      // (double)(S / n)
-                        const double qd = floor(__dmul_rn(__dadd_rn((double)Q, 0.5), rn));      // (double)(Q / n)
-                        const double mm = __dmul_rn(md, md);
-                        const double v = __dadd_rn(qd, -mm);
-                        const double pix = (double)((wcur >> (8 * j)) & 0xFFu);
-                        const double t = __dadd_rn(pix, __dmul_rn(md, p.km1));
-                        const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), v);
-                        const double lhs = __dmul_rn(t, t);
-                        if (KNEG) fg = (t <= 0.0) && (lhs >= rhs);
-                        else        fg = (t <= 0.0) || (lhs <= rhs);
-                    }
-                    bits |= fg << (8 * j);
-                }
-            }
-            if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) bits ^= 0x01010101u;
-            uint8_t *orow = out + (int64_t)y * p.out_pitch + gx;
-            if (gx + 3 < W) {
-                uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
-                if (p.flags & B200MRC_SAUVOLA_OR_INTO) bits |= *o32;
-                *o32 = bits;
-            } else {
-                for (int j = 0; j < SK && gx + j < W; j++) {
-                    uint8_t b = (uint8_t)((bits >> (8 * j)) & 0xFFu);
-                    if (p.flags & B200MRC_SAUVOLA_OR_INTO) b |= orow[j];
-                    orow[j] = b;
-                }
-            }
-        }
-
-        // ---- slide the window rows for the next output row
-#pragma unroll
-        for (int j = 0; j < SK; j++) {
-            const uint32_t a = (wenter >> (8 * j)) & 0xFFu, b = (wleave >> (8 * j)) & 0xFFu;
-            cs[j] += a - b;
-            cq[j] += a * a - b * b;
-        }
-        wcur = wnext;
-    }
-}
-
-
-// ---- production form: warp-local prefixes, ONE barrier per row ------------------------------------------------
-// The CTA-wide prefix above costs two barriers and 8 warp totals folded in by every thread per row.  Here every
+// ---- warp-local prefixes, ONE barrier per row ---------------------------------------------------------------
+// A CTA-wide prefix would cost two barriers and 8 warp totals folded in by every thread per row.  Here every
 // warp publishes the prefix of ITS OWN 128 columns (L) plus its total (WT); a window [clo, chi) spans at most three
 // warps (window <= 255), so   S = L[chi] - L[clo] + WT[wlo] (+ WT[wlo+1]),   the WT indices being row-invariant per
 // pixel (an all-zero entry stands for "same warp").  The buffers alternate with the row, the row loop is unrolled
@@ -332,7 +136,9 @@ __global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams
         sWT[tid * WTN + 8] = make_uint2(0u, 0u);
     }
 
-    // loads run two rows ahead of their use (see k_sauvola_mask)
+    // loads run two rows ahead of their use (L2/HBM latency >> one row step): stage A feeds the next iteration, stage B
+    // the one after.  Words are loaded raw through three running row pointers and masked (columns outside the page read
+    // as 0) only when they are consumed, so nothing waits on a load in the iteration that issues it.
     const bool lok = gx >= 0 && gx < W;
     const uint32_t lmask = !lok ? 0u : (W - gx >= 4 ? 0xffffffffu : (1u << (8 * (W - gx))) - 1u);
     const uint8_t *pe = in + (int64_t)(by0 + 1 + p.u) * p.in_pitch + gx;      // entering row of the next load_upd
@@ -384,7 +190,9 @@ __global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams
         if (is_out) {
             const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
             uint32_t bits = 0;
-            // S/n and Q/n on the FP64 pipe: floor((a + 0.5) * (1/n)) == a / n exactly (see k_sauvola_mask)
+            // S/n and Q/n on the (otherwise idle) FP64 pipe: floor((a + 0.5) * (1/n)) == a / n exactly, because (a + 0.5)/n is
+            // at least 1/(2n) away from every integer while the double product is accurate to 2^-52 relative (a < 2^32,
+            // n <= 65025).  The quotients come out as the doubles the test needs.
             if (nx_uniform && ny != ny_cached) { rn_u = 1.0 / (double)(nx0 * ny); ny_cached = ny; }
             uint32_t S[SK], Q[SK];
 #pragma unroll
@@ -452,6 +260,14 @@ __global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams
 
 }  // namespace
 
+bool sauvola_fused_ok(const uint8_t *src, int64_t src_pitch, int64_t src_stride, int C, const uint8_t *out, int64_t out_pitch,
+                      int64_t out_stride, int W, int H, int ww, int wh, double k, int flags);
+int launch_sauvola_fused(const uint8_t *src, int64_t src_pitch, int64_t src_stride, int C,
+                         uint8_t *gray, int64_t gray_pitch, int64_t gray_stride,
+                         uint8_t *out, int64_t out_pitch, int64_t out_stride,
+                         int W, int H, int N, int ww, int wh, double k, double Rr, const double *sigma, int flags, cudaStream_t st);
+bool threshold_path_legacy();
+
 }  // namespace b200mrc
 
 using namespace b200mrc;
@@ -471,6 +287,12 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
         (in_page_stride & 3) || (out_page_stride & 3) || in_pitch < width || out_pitch < width)
         return B200MRC_ERR_ALIGNMENT;
 
+    // rows that TMA can move: the 8-columns-per-thread kernel of sauvola_fused.cu in its direct (gray in) form
+    if (!threshold_path_legacy() && n_pages <= 65535 &&
+        sauvola_fused_ok(in, in_pitch, in_page_stride, 1, out, out_pitch, out_page_stride, width, height, window_width, window_height, k, flags))
+        return launch_sauvola_fused(in, in_pitch, in_page_stride, 1, nullptr, 0, 0, out, out_pitch, out_page_stride, width, height, n_pages,
+                                    window_width, window_height, k, R, nullptr, flags, (cudaStream_t)stream);
+
     SauvolaParams p;
     p.in = in; p.in_pitch = in_pitch; p.in_stride = in_page_stride;
     p.out = out; p.out_pitch = out_pitch; p.out_stride = out_page_stride;
@@ -481,7 +303,7 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     const int sw_max = (SE - p.ext_left - p.r) / 4 * 4;          // >= 768
     p.n_strips = cdiv(width, sw_max);
     p.strip_w = (cdiv(width, p.n_strips) + 3) / 4 * 4;
-    { const char *e = getenv("B200MRC_SAUVOLA_BAND"); p.band_h = e ? atoi(e) : 128; if (p.band_h < 16) p.band_h = 16; }
+    p.band_h = 128;
     p.n_bands = cdiv(height, p.band_h);
     p.km1 = k - 1.0;
     p.k2 = k * k / R / R;                                         // sauvola.pyx:60
@@ -490,24 +312,13 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
 
     dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_pages);
     { ProfScope _ps("k_sauvola_mask", (cudaStream_t)stream);
-      const char *mb = getenv("B200MRC_SAUVOLA_MINB");
-      const int minb = mb ? atoi(mb) : 4;
-      const char *pf = getenv("B200MRC_SAUVOLA_PREFIX");          // "cta": the two-barrier CTA-wide prefix (A/B runs)
       const bool wide = window_width > 128;                        // a window may then span three warps
-      if (pf && !strcmp(pf, "cta")) {
-          if (p.kneg) k_sauvola_mask<true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-          else if (minb == 5) k_sauvola_mask<false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-          else if (minb == 6) k_sauvola_mask<false, 6><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-          else if (minb == 3) k_sauvola_mask<false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-          else k_sauvola_mask<false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      } else if (p.kneg) {
+      if (p.kneg) {
           if (wide) k_sauvola_mask_w<true, true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
           else k_sauvola_mask_w<true, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
       } else if (wide) {
           k_sauvola_mask_w<false, true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      } else if (minb == 5) k_sauvola_mask_w<false, false, 5><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else if (minb == 3) k_sauvola_mask_w<false, false, 3><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
-      else k_sauvola_mask_w<false, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
+      } else k_sauvola_mask_w<false, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

@@ -146,30 +146,39 @@ def downsample_plan(w, h, c, factor, filter=BICUBIC):
     return None, True
 
 
-class _Workspace:
-    def __init__(self):
-        self.t = None
-
-    def get(self, nbytes, device):
-        if self.t is None or self.t.numel() < nbytes or self.t.device != torch.device(device):
-            self.t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        return self.t
-
-
 class MrcEngine:
-    """One engine per process/GPU.  Methods taking `Plane`s are asynchronous on the current stream."""
+    """One engine per GPU (mrc.get_engine(device)).  Methods taking `Plane`s are asynchronous on the current stream.
+
+    Scratch memory is private to (stage, stream): two streams -- or two host threads on their own streams -- may run
+    stages of the same engine concurrently; calls on ONE stream are ordered by the stream.  The optimise workspace is
+    never shared with another stage (its mailbox rows must not be overwritten between the FIR pass and the sweep)."""
 
     def __init__(self, device=None):
         _require_cuda()
         L.lib()
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
-        self._ws = _Workspace()
+        self._ws = {}
         self._lock = threading.Lock()
 
     # ------------------------------------------------------------------ raw stages (device planes)
-    def workspace(self, nbytes):
-        t = self._ws.get(nbytes, self.device)
+    def workspace(self, nbytes, stage='scratch'):
+        key = (stage, torch.cuda.current_stream(self.device).cuda_stream)
+        with self._lock:
+            t = self._ws.get(key)
+            if t is None or t.numel() < nbytes:
+                t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+                self._ws[key] = t
         return C.c_void_p(t.data_ptr()), t.numel()
+
+    def threshold_mask(self, img, out, window_w, window_h=None, k=0.34, R=128.0, sigma_dev=None, flags=0):
+        """create_threshold_mask (mrc.py:300-329): gray -> conditional blur -> Sauvola in one fused pass.
+        img: 1- or 3-channel Plane; sigma_dev: float64 device tensor [N] or None (no blur)."""
+        need = L.lib().b200mrc_threshold_workspace_bytes(img.w, img.h, img.n)
+        wp, wb = self.workspace(need, 'threshold')
+        sp = C.c_void_p(sigma_dev.data_ptr()) if sigma_dev is not None else None
+        L.check(L.lib().b200mrc_threshold_mask(img.ptr, img.pitch, img.page_stride, img.c, out.ptr, out.pitch, out.page_stride,
+                                               img.w, img.h, img.n, window_w, window_h or window_w, float(k), float(R), sp, flags,
+                                               wp, wb, _stream_ptr()), 'b200mrc_threshold_mask')
 
     def sauvola(self, gray, out, window_w, window_h=None, k=0.34, R=128.0, flags=0):
         L.check(L.lib().b200mrc_sauvola(gray.ptr, gray.pitch, gray.page_stride, out.ptr, out.pitch, out.page_stride,
@@ -185,20 +194,20 @@ class MrcEngine:
         """-> float64 device tensor [N] (mrc.py:273-296 on every page)."""
         sigma = torch.empty(img.n, dtype=torch.float64, device=self.device)
         need = L.lib().b200mrc_noise_workspace_bytes(img.w, img.h, img.n)
-        wp, wb = self.workspace(need)
+        wp, wb = self.workspace(need, 'noise')
         L.check(L.lib().b200mrc_estimate_noise(img.ptr, img.pitch, img.page_stride, img.c, img.w, img.h, img.n,
                                                C.c_void_p(sigma.data_ptr()), wp, wb, _stream_ptr()), 'b200mrc_estimate_noise')
         return sigma
 
     def denoise(self, mask, mincnt=4, n_size=2):
         need = L.lib().b200mrc_denoise_workspace_bytes(mask.w, mask.h, mask.n)
-        wp, wb = self.workspace(need)
+        wp, wb = self.workspace(need, 'denoise')
         L.check(L.lib().b200mrc_denoise(mask.ptr, mask.pitch, mask.page_stride, mask.w, mask.h, mask.n, mincnt, n_size,
                                         wp, wb, _stream_ptr()), 'b200mrc_denoise')
 
     def optimise(self, mask, img, out_fg=None, n_fg=3, out_bg=None, n_bg=10):
         need = L.lib().b200mrc_optimise_workspace_bytes(img.w, img.h, img.n)
-        wp, wb = self.workspace(need)
+        wp, wb = self.workspace(need, 'optimise')
         f = (out_fg.ptr, out_fg.pitch, out_fg.page_stride) if out_fg is not None else (None, 0, 0)
         b = (out_bg.ptr, out_bg.pitch, out_bg.page_stride) if out_bg is not None else (None, 0, 0)
         L.check(L.lib().b200mrc_optimise(mask.ptr, mask.pitch, mask.page_stride, img.ptr, img.pitch, img.page_stride, img.c,
@@ -229,7 +238,7 @@ class MrcEngine:
 
     def resample(self, plan, src, dst):
         need = plan.workspace_bytes(src.n)
-        wp, wb = self.workspace(need)
+        wp, wb = self.workspace(need, 'resample')
         L.check(L.lib().b200mrc_resample(plan.handle, src.ptr, src.pitch, src.page_stride, dst.ptr, dst.pitch,
                                          dst.page_stride, src.n, wp, wb, _stream_ptr()), 'b200mrc_resample')
 
@@ -314,13 +323,13 @@ class DecomposeBatch:
 
     # stage-by-stage form of run(): the same kernels through the per-stage C-ABI entry points, with a
     # CUDA event recorded between stages so a profile of the step comes from the step itself
-    STAGES = ('noise', 'gray_blur', 'sauvola', 'denoise', 'optimise', 'fg_thumbnail', 'bg_thumbnail')
+    STAGES = ('noise', 'threshold', 'denoise', 'optimise', 'fg_thumbnail', 'bg_thumbnail')
 
     def run_staged(self, window, k=0.34, R=128.0, denoise_mask=DENOISE_FAST, sigma=None, events=None):
         """events: None or a dict filled with stage -> (start_event, end_event)."""
         eng = self.eng
-        if getattr(self, '_gray', None) is None:
-            self._gray = Plane(self.n, self.h, self.w, 1, eng.device)
+        if getattr(self, '_staged', None) is None:
+            self._staged = True
             self._fg_full = Plane(self.n, self.h, self.w, self.c, eng.device) if (self.fg_plan and not self.mask_only) else None
             self._bg_full = Plane(self.n, self.h, self.w, self.c, eng.device) if (self.bg_plan and not self.mask_only) else None
 
@@ -339,8 +348,7 @@ class DecomposeBatch:
         else:
             self.sigma_in.copy_(torch.as_tensor(np.asarray(sigma, np.float64)))
             sig = self.sigma_in
-        stage('gray_blur', lambda: eng.gray_blur(self.img, self._gray, sig))
-        stage('sauvola', lambda: eng.sauvola(self._gray, self.mask, window, window, k, R))
+        stage('threshold', lambda: eng.threshold_mask(self.img, self.mask, window, window, k, R, sig))
         if denoise_mask == DENOISE_FAST:
             stage('denoise', lambda: eng.denoise(self.mask, 4, 2))
         if self.mask_only:
@@ -368,17 +376,20 @@ class StreamedDecomposer:
     pinned."""
 
     def __init__(self, eng, n_pages, h, w, c, chunk=4, bg_downsample=None, fg_downsample=None, mask_only=False,
-                 buffers=4, compute_streams=2):
+                 buffers=4, compute_streams=2, packed_mask=False):
         self.eng, self.n, self.h, self.w, self.c = eng, n_pages, h, w, c
         self.chunk = max(1, min(chunk, n_pages))
         n_chunks = (n_pages + self.chunk - 1) // self.chunk
         self.nb = max(1, min(buffers, n_chunks))
         self.batches = [eng.make_batch(self.chunk, h, w, c, bg_downsample, fg_downsample, mask_only) for _ in range(self.nb)]
         self.mask_only = mask_only
+        # packed_mask: the mask comes back as PIL mode-'1' rows (b200mrc_pack_mask: ceil(W/8) bytes per row, what
+        # encode_mrc_mask hands to the JBIG2/PNG encoder, mrc.py:474-520) -- 8x fewer D2H bytes than the bool plane
+        self.packed_mask = packed_mask
         self.s_in, self.s_out = torch.cuda.Stream(device=eng.device), torch.cuda.Stream(device=eng.device)
         self.s_cmp = [torch.cuda.Stream(device=eng.device) for _ in range(max(1, min(compute_streams, self.nb)))]
         b = self.batches[0]
-        self.out_shapes = dict(mask=(h, w), fg=None if mask_only else (b.fg.h, b.fg.w * c), bg=None if mask_only else (b.bg.h, b.bg.w * c))
+        self.out_shapes = dict(mask=(h, (w + 7) // 8) if packed_mask else (h, w), fg=None if mask_only else (b.fg.h, b.fg.w * c), bg=None if mask_only else (b.bg.h, b.bg.w * c))
         self.errors = set(b.errors)
         # contiguous device staging per buffer (planes whose pitch equals the row length need none)
         dev = eng.device
@@ -386,11 +397,16 @@ class StreamedDecomposer:
         def stage(plane):
             return None if plane.pitch == plane.w * plane.c else torch.empty((self.chunk, plane.h, plane.w * plane.c), dtype=torch.uint8, device=dev)
         self.st_in = [stage(b_.img) for b_ in self.batches]
-        self.st_out = [dict(mask=stage(b_.mask), fg=None if mask_only else stage(b_.fg), bg=None if mask_only else stage(b_.bg))
+        def mask_stage(plane):
+            if packed_mask:
+                return torch.empty((self.chunk, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
+            return stage(plane)
+        self.st_out = [dict(mask=mask_stage(b_.mask), fg=None if mask_only else stage(b_.fg), bg=None if mask_only else stage(b_.bg))
                        for b_ in self.batches]
 
     def alloc_outputs(self):
-        """Pinned host result buffers: mask [N,H,W] u8 (0/1), fg [N,fh,fw*C], bg [N,bh,bw*C]."""
+        """Pinned host result buffers: mask [N,H,W] u8 (0/1) -- or [N,H,ceil(W/8)] packed rows with packed_mask --,
+        fg [N,fh,fw*C], bg [N,bh,bw*C]."""
         o = {'mask': torch.empty((self.n,) + self.out_shapes['mask'], dtype=torch.uint8).pin_memory()}
         if not self.mask_only:
             o['fg'] = torch.empty((self.n,) + self.out_shapes['fg'], dtype=torch.uint8).pin_memory()
@@ -444,7 +460,12 @@ class StreamedDecomposer:
                 b.run(window, k, R, denoise_mask)                  # b200mrc_decompose on the chunk (a short tail chunk recomputes stale pages: harmless)
                 for name in names:
                     plane, st = getattr(b, name), self.st_out[slot][name]
-                    if st is not None:
+                    if name == 'mask' and self.packed_mask:
+                        nb = (plane.w + 7) // 8
+                        L.check(L.lib().b200mrc_pack_mask(plane.ptr, plane.pitch, plane.page_stride, C.c_void_p(st.data_ptr()), nb,
+                                                          plane.h * nb, plane.w, plane.h, m, 0, C.c_void_p(sc.cuda_stream)),
+                                'b200mrc_pack_mask')
+                    elif st is not None:
                         row = plane.w * plane.c
                         _copy2d(st.data_ptr(), row, plane.t.data_ptr(), plane.pitch, row, m * plane.h, L.COPY_D2D, sc)
                 cmp_done[i] = sc.record_event()

@@ -19,14 +19,32 @@ from .engine import DENOISE_NONE, DENOISE_FAST, DENOISE_BREGMAN
 
 RECODE_RUNTIME_WARNING_TOO_SMALL_TO_DOWNSAMPLE = 'too-small-to-downsample'    # const.py:38
 
-_engine = None
+_engines = {}
 
 
-def get_engine():
-    global _engine
-    if _engine is None:
-        _engine = E.MrcEngine()
-    return _engine
+def get_engine(device=None):
+    """The engine of `device` (default: the current CUDA device); one per GPU, so a process that drives several
+    GPUs gets an engine for each of them."""
+    E._require_cuda()
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    eng = _engines.get(idx)
+    if eng is None:
+        eng = _engines[idx] = E.MrcEngine('cuda:%d' % idx)
+    return eng
+
+
+MAX_BLUR_SIGMA_EST = (128.5 / 4) / 0.1          # blur radius int(4 * 0.1 * sigma_est + 0.5) must stay <= 128
+
+
+def _check_sigma(sigmas):
+    """The pre-blur kernels cover radius <= 128 (sigma_est < 321: far beyond any scan); anything larger would leave the
+    gray plane unwritten, so it is an error rather than a silent garbage mask."""
+    bad = [float(v) for v in np.atleast_1d(sigmas) if v >= MAX_BLUR_SIGMA_EST]
+    if bad:
+        raise L.B200MrcError('estimated noise sigma %.1f needs a Gaussian pre-blur of radius > 128, which the engine does '
+                             'not implement' % bad[0])
 
 
 def threshold_image(img, dpi, k=0.34):
@@ -68,6 +86,30 @@ def _needs_sigma(ratio, inv_ratio):
     return (ratio < 0.3 or inv_ratio < 0.3) and not (inv_ratio > 0.2 and ratio < 0.2)
 
 
+def _iter_text_lines(hocr_word_data, image_width, image_height, downsample):
+    """Integer boxes (left, top, right, bottom) of the hOCR text lines create_hocr_mask looks at (mrc.py:194-221):
+    lines with text and a mean word confidence of at least 20, scaled by 1/downsample, truncated to int; empty boxes are
+    dropped silently, inverted boxes and boxes leaving the page with the reference's diagnostics on stderr."""
+    import sys
+    for paragraph in hocr_word_data or ():
+        for line in paragraph['lines']:
+            words = line['words']
+            confs = [w['confidence'] for w in words]
+            mean_conf = sum(confs) / len(confs) if confs else 0
+            if mean_conf < 20 or not ' '.join(w['text'] for w in words).strip():
+                continue
+            box = [int(v) if downsample is None else int(v / downsample) for v in line['bbox']]
+            left, top, right, bottom = box
+            if left == right or top == bottom:
+                continue
+            if left >= right or top >= bottom:
+                print('Invalid bounding box: (%d, %d, %d, %d)' % tuple(box), file=sys.stderr)
+            elif left < 0 or top < 0 or right > image_width or bottom > image_height:
+                print('Invalid bounding box outside image: (%d, %d, %d, %d)' % tuple(box), file=sys.stderr)
+            else:
+                yield tuple(box)
+
+
 def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, timing_data=None):
     """mrc.py:188-270 on the device.  img: gray Plane (the plain 'L' page, n = 1); mask_arr: mask Plane, modified in
     place.  Per text line: Sauvola (k = 0.1) on the crop and on the inverted crop, polarity picked by fill ratio and,
@@ -76,34 +118,8 @@ def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, t
     sigma kernel and the pastes (in line order, so overlapping boxes resolve like the reference's loop); the host
     only takes the per-line decisions (two small D2H reads per page)."""
     import ctypes as C
-    import sys
     t = time()
-    lines = []
-    if hocr_word_data:
-        image_width, image_height = img.w, img.h
-        for paragraph in hocr_word_data:
-            for line in paragraph['lines']:
-                coords = line['bbox']
-                line_text = ' '.join([word['text'] for word in line['words']])
-                line_confs = [word['confidence'] for word in line['words']]
-                line_conf = sum(line_confs) / len(line_confs) if len(line_confs) else 0
-                if line_text.strip() == '' or line_conf < 20:
-                    continue
-                if downsample is not None:
-                    coords = [int(x / downsample) for x in coords]
-                else:
-                    coords = [int(x) for x in coords]
-                left, top, right, bottom = coords
-                # This can happen if we downsample and round to int
-                if left == right or top == bottom:
-                    continue
-                if (left >= right) or (top >= bottom):
-                    print('Invalid bounding box: (%d, %d, %d, %d)' % (left, top, right, bottom), file=sys.stderr)
-                    continue
-                if (left < 0) or (right > image_width) or (top < 0) or (bottom > image_height):
-                    print('Invalid bounding box outside image: (%d, %d, %d, %d)' % (left, top, right, bottom), file=sys.stderr)
-                    continue
-                lines.append((left, top, right, bottom))
+    lines = list(_iter_text_lines(hocr_word_data, img.w, img.h, downsample))
     if lines:
         eng = get_engine()
         lib = L.lib()
@@ -228,16 +244,12 @@ def create_mrc_hocr_components(image, hocr_word_data,
     sigma_est = float(sigma_dev.cpu()[0])              # synchronises: 'est_1' is a true stage time
     if timing_data is not None:
         timing_data.append(('est_1', time() - t))
-    gray = E.Plane(1, height_, width_, 1, eng.device)
-    if sigma_est > 1.0:
-        t = time()
-        eng.gray_blur(src, gray, sigma_dev)
-        if timing_data is not None:
-            timing_data.append(('blur_1', _sync_time(t)))
-    else:
-        eng.gray_blur(src, gray, None)
+    _check_sigma(sigma_est)
+    if sigma_est > 1.0 and timing_data is not None:
+        timing_data.append(('blur_1', 0.0))                # the pre-blur is fused into the threshold pass below
     t = time()
-    eng.sauvola(gray, mask, E.window_for_dpi(dpi), k=0.34, R=128.0, flags=L.SAUVOLA_OR_INTO if n_lines else 0)   # mask_arr |= thres_arr
+    eng.threshold_mask(src, mask, E.window_for_dpi(dpi), k=0.34, R=128.0, sigma_dev=sigma_dev if sigma_est > 1.0 else None,
+                       flags=L.SAUVOLA_OR_INTO if n_lines else 0)                                       # mask_arr |= thres_arr
     if timing_data is not None:
         timing_data.append(('threshold', _sync_time(t)))
 
@@ -302,9 +314,12 @@ def downsample_image(image, downsample):
     """The page pre-step of recode.py:368-372 -- image.thumbnail((w/downsample, h/downsample), resample=LANCZOS,
     reducing_gap=None) -- on the device.  image: PIL 'L' / 'RGB'; returns a new PIL image (Pillow resizes in place)."""
     from PIL import Image
-    if image.mode not in ('L', 'RGB'):
-        image = image.convert('RGB')
     w, h = image.size
+    if image.mode not in ('L', 'RGB'):
+        # the reference thumbnails in the image's own mode (Pillow picks NEAREST for '1' / 'P'); rare: left to Pillow
+        image = image.copy()
+        image.thumbnail((w / downsample, h / downsample), resample=Image.LANCZOS, reducing_gap=None)
+        return image
     out = get_engine().thumbnail_np(np.asarray(image), w / downsample, h / downsample, reducing_gap=None, filter=E.LANCZOS)
     return Image.fromarray(out)
 
@@ -352,6 +367,7 @@ def decompose_pages(pages, dpi=None, window=None, bg_downsample=None, fg_downsam
             create_hocr_mask(gray if c != 1 else page_img, E.PageView(batch.mask, i), hd, downsample=downsample, dpi=dpi)
     batch.run(window if window is not None else E.window_for_dpi(dpi), denoise_mask=denoise_mask, sigma=sigma, or_into_mask=or_into)
     res = dict(mask=batch.mask.numpy(np.bool_), sigma=batch.sigma.cpu().numpy(), errors=set(batch.errors))
+    _check_sigma(res['sigma'])
     if not mask_only:
         res['fg'] = batch.fg.numpy()
         res['bg'] = batch.bg.numpy()

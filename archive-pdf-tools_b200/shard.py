@@ -26,20 +26,23 @@ def scatter_pages(pages, page_shape, n_pages, src=0, device=None):
     mine = shard_indices(n_pages, rank, world)
     out = torch.empty((len(mine),) + tuple(page_shape), dtype=torch.uint8, device=device)
     if rank == src:
-        reqs = []
+        ops, keep = [], []
         for r in range(world):
             idx = shard_indices(n_pages, r, world)
             if not idx:
                 continue
-            chunk = pages[idx].contiguous()
+            chunk = pages[r::world].contiguous()             # pages i = r (mod world), in page order
             if r == src:
                 out.copy_(chunk)
             else:
-                reqs.append(dist.isend(chunk, dst=r))
-        for q in reqs:
-            q.wait()
+                keep.append(chunk)
+                ops.append(dist.P2POp(dist.isend, chunk, r))
+        if ops:                                              # one grouped launch: all sends in flight at once (NCCL group)
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
     elif mine:
-        dist.recv(out, src=src)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, out, src)]):
+            q.wait()
     return out
 
 
@@ -49,19 +52,25 @@ def gather_results(local, n_pages, dst=0):
     rank, world = dist.get_rank(), dist.get_world_size()
     if rank == dst:
         full = torch.empty((n_pages,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        ops, bufs = [], {}
         for r in range(world):
-            idx = shard_indices(n_pages, r, world)
-            if not idx:
+            cnt = len(range(r, n_pages, world))
+            if not cnt:
                 continue
             if r == dst:
-                full[idx] = local
+                full[r::world] = local
             else:
-                buf = torch.empty((len(idx),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-                dist.recv(buf, src=r)
-                full[idx] = buf
+                bufs[r] = torch.empty((cnt,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+                ops.append(dist.P2POp(dist.irecv, bufs[r], r))
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        for r, buf in bufs.items():
+            full[r::world] = buf
         return full
     if local.shape[0]:
-        dist.send(local.contiguous(), dst=dst)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+            q.wait()
     return None
 
 

@@ -65,6 +65,11 @@ B200MRC_API int         b200mrc_version(void);
 B200MRC_API const char *b200mrc_error_string(int status);
 /* number of CUDA kernels this library has launched in the calling process (bench bookkeeping) */
 B200MRC_API uint64_t    b200mrc_launch_count(void);
+/* Tuning knobs for A/B runs and tests (kernel forms, band sizes, page groups ...; INTEGRATION.md lists the names).  Each
+ * knob is initialised once per process from the environment variable B200MRC_<NAME>; set_tuning changes it for the
+ * launches that follow (process-wide, atomic).  Unknown names return B200MRC_ERR_INVALID. */
+B200MRC_API int         b200mrc_set_tuning(const char *name, int value);
+B200MRC_API int         b200mrc_get_tuning(const char *name, int *value);
 /* Per-kernel device timing: while enabled, every kernel launch of this library is bracketed by a CUDA
  * event pair on its own stream.  b200mrc_profile_report synchronises and writes "kernel,launches,total_ms"
  * lines into buf (returns the full length); enable(0/1) also clears the records. */
@@ -112,6 +117,19 @@ B200MRC_API int b200mrc_estimate_noise(const uint8_t *in, int64_t in_pitch, int6
 B200MRC_API int b200mrc_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_page_stride, int channels,
                       uint8_t *gray_out, int64_t gray_pitch, int64_t gray_page_stride,
                       int width, int height, int n_pages, const double *sigma, void *stream);
+
+/* A1+A2+A4+A5+A6(+A7)  create_threshold_mask (mrc.py:300-329) in one pass: convert('L') -> conditional Gaussian
+ * pre-blur (sigma = 0.1 * sigma[p] where sigma[p] > 1.0; `sigma` is a DEVICE array or NULL) -> uint8 truncation ->
+ * binarise_sauvola + invert -> out (or out |= with B200MRC_SAUVOLA_OR_INTO).  `in` has 1 or 3 channels.  With
+ * 16-byte aligned rows this is a single fused kernel (TMA-fed, no gray plane pass); otherwise it runs
+ * b200mrc_gray_blur + b200mrc_sauvola.  workspace: b200mrc_threshold_workspace_bytes() (a gray delay-line plane). */
+B200MRC_API size_t b200mrc_threshold_workspace_bytes(int width, int height, int n_pages);
+B200MRC_API int b200mrc_threshold_mask(const uint8_t *in, int64_t in_pitch, int64_t in_page_stride, int channels,
+                           uint8_t *out, int64_t out_pitch, int64_t out_page_stride,
+                           int width, int height, int n_pages,
+                           int window_width, int window_height, double k, double R,
+                           const double *sigma, int flags,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* A8  fast_mask_denoise (optimiser.pyx:436-472), in place, exact raster-order semantics.
  * Implemented for the only configuration the reference uses: mincnt = 4, n_size = 2

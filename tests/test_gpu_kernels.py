@@ -6,6 +6,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def tuning():
+    """set(name, value) changes a b200mrc tuning knob (b200mrc_set_tuning) for the test and restores it afterwards."""
+    from archive_pdf_tools_b200 import _lib
+    saved = {}
+
+    def set_(name, value):
+        saved.setdefault(name, _lib.get_tuning(name))
+        _lib.set_tuning(name, value)
+    yield set_
+    for k, v in saved.items():
+        _lib.set_tuning(k, v)
+
+
 def _plane(eng, arr, c=None):
     from archive_pdf_tools_b200 import Plane
     a = np.ascontiguousarray(arr)
@@ -178,16 +192,16 @@ def test_optimise_text_page_many_strips(eng, orc, synth):
     assert np.array_equal(bg.numpy()[0], orc.optimise(~mask, page, 10))
 
 
-@pytest.mark.parametrize('variant', [{'B200MRC_IIRW_MODE': 'trio'}, {'B200MRC_IIRW_MODE': 'trio', 'B200MRC_IIRW_TPC': '1'},
-                                     {'B200MRC_IIRW_MODE': 'trio', 'B200MRC_IIRW_TPC': '3'},
-                                     {'B200MRC_IIRW_MODE': 'single', 'B200MRC_IIRW_FEED': 'tma'},
-                                     {'B200MRC_IIRW_MODE': 'single', 'B200MRC_IIRW_FEED': 'async'}],
+@pytest.mark.parametrize('variant', [{'IIRW_MODE': 'trio'}, {'IIRW_MODE': 'trio', 'IIRW_TPC': '1'},
+                                     {'IIRW_MODE': 'trio', 'IIRW_TPC': '3'},
+                                     {'IIRW_MODE': 'single', 'IIRW_FEED': 'tma'},
+                                     {'IIRW_MODE': 'single', 'IIRW_FEED': 'async'}],
                          ids=['trio', 'trio1', 'trio3', 'single-tma', 'single-async'])
-def test_optimise_sweep_variants(eng, orc, synth, monkeypatch, variant):
+def test_optimise_sweep_variants(eng, orc, synth, tuning, variant):
     """Every form of the row-sequential sweep (launcher picks by batch size; forced here) against the oracle:
     ragged strip widths, many strips, gray and RGB, random masks and a text page, several pages per launch."""
     for k, v in variant.items():
-        monkeypatch.setenv(k, v)
+        tuning(k, v)
     rng = np.random.default_rng(77)
     for (h, w), c in [((37, 128), 3), ((64, 129), 3), ((90, 700), 1), ((131, 397), 3), ((70, 1027), 1), ((1, 300), 3), ((5, 4), 3)]:
         dens = (0.0, 0.05, 0.5, 1.0)
@@ -211,10 +225,39 @@ def test_optimise_sweep_variants(eng, orc, synth, monkeypatch, variant):
         assert np.array_equal(bg.numpy()[i], orc.optimise(~mks[i], pages[i], 10))
 
 
-@pytest.mark.parametrize('prefix', ['warp', 'cta'])
-def test_sauvola_prefix_variants(eng, orc, monkeypatch, prefix):
-    """Both horizontal-prefix forms of the Sauvola kernel (warp-local: production; CTA-wide: kept for A/B runs)."""
-    monkeypatch.setenv('B200MRC_SAUVOLA_PREFIX', prefix)
+@pytest.mark.parametrize('fill', [0xFF, 0xEE, 0x11])
+def test_optimise_mailbox_survives_foreign_workspace_bytes(eng, orc, tuning, fill):
+    """The sweep's strip hand-off rows live in a workspace that other stages (and callers) may overwrite between
+    launches.  Every launch epoch 1..255 (and the wrap) is run on a workspace pre-filled with a byte pattern whose
+    tag nibbles equal some epoch: the FIR pass clears the rows, so no stale or foreign word can be taken for a hand-off."""
+    import torch
+    rng = np.random.default_rng(fill)
+    h, w = 24, 300                                                # 3 strips of 128 columns
+    masks = np.stack([rng.random((h, w)) < d for d in (0.05, 0.5)])
+    imgs = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    m = _plane(eng, masks); src = _plane(eng, imgs)
+    fg = _empty(eng, 2, h, w, 3); bg = _empty(eng, 2, h, w, 3)
+    exp_f = [orc.optimise(masks[i], imgs[i], 3) for i in range(2)]
+    exp_b = [orc.optimise(~masks[i], imgs[i], 10) for i in range(2)]
+    eng.optimise(m, src, fg, 3, bg, 10)                           # allocates the workspace
+    ws = eng._ws[('optimise', torch.cuda.current_stream(eng.device).cuda_stream)]
+    for mode in ('trio', 'single'):
+        tuning('IIRW_MODE', mode)
+        for it in range(260):
+            ws.fill_(fill)
+            eng.optimise(m, src, fg, 3, bg, 10)
+            if it % 13 == 0 or it > 250:
+                gf, gb = fg.numpy(), bg.numpy()
+                for i in range(2):
+                    assert np.array_equal(gf[i], exp_f[i]) and np.array_equal(gb[i], exp_b[i]), (mode, it, i)
+
+
+@pytest.mark.parametrize('path', ['fused', 'legacy'])
+def test_sauvola_both_paths(eng, orc, tuning, path):
+    """Gray planes with 16-byte aligned rows take the 8-columns-per-thread TMA-fed kernel (sauvola_fused.cu, direct form);
+    everything else -- and THRESHOLD_PATH=legacy -- the general 4-byte kernel (sauvola.cu).  Window widths around the
+    warp spans (127..129), widest window, several strips per row."""
+    tuning('THRESHOLD_PATH', path)
     rng = np.random.default_rng(11)
     for h, w in [(150, 2600), (260, 1100), (40, 130)]:
         img = np.clip(rng.normal(190, 45, (2, h, w)), 0, 255).astype(np.uint8)
@@ -223,7 +266,99 @@ def test_sauvola_prefix_variants(eng, orc, monkeypatch, prefix):
             eng.sauvola(src, dst, ww, ww, k=k)
             got = dst.numpy(np.bool_)
             for i in range(2):
-                assert np.array_equal(got[i], orc.sauvola(img[i], ww, ww, k=k)), (prefix, h, w, ww, i)
+                assert np.array_equal(got[i], orc.sauvola(img[i], ww, ww, k=k)), (path, h, w, ww, i)
+
+
+def _threshold_expected(orc, page, sig_est, ww, wh, k=0.34):
+    gray = page if page.ndim == 2 else orc.rgb2gray(page)
+    if sig_est is not None and sig_est > 1.0:
+        gray = orc.gauss_blur(gray.astype(np.float32), sig_est * 0.1).astype(np.uint8)
+    return orc.sauvola(gray, ww, wh, k=k)
+
+
+@pytest.mark.parametrize('shape,rgb', [((70, 64), True), ((90, 131), False), ((300, 1003), True), ((131, 2000), False),
+                                       ((420, 2550), True), ((64, 3000), True), ((1, 1), True), ((9, 40), False)])
+def test_threshold_mask_matches_oracle(eng, orc, shape, rgb):
+    """create_threshold_mask as one fused kernel (b200mrc_threshold_mask): gray conversion, per-page blur decision
+    (radius 0, 1, 2 in-kernel; radius > 2 through the tiled pre-blur; NaN / <= 1.0: none), Sauvola.  Small pages take
+    the two-pass fallback behind the same entry point."""
+    import torch
+    h, w = shape
+    rng = np.random.default_rng(h * 31 + w)
+    sig_est = [0.5, 1.1, 1.3, 3.4, 4.0, 6.2, 9.0, 26.0, float('nan')]                    # radii 0 0 1 1 2 2 4 10 -
+    n = len(sig_est)
+    base = np.clip(rng.normal(180, 50, (n, h, w)), 0, 255)
+    base[:, : h // 3, : w // 2] = rng.integers(0, 256, (n, h // 3, w // 2))
+    base[:, -(h // 4 + 1):, :] = 255                                                     # a saturated flat band
+    if rgb:
+        pages = np.clip(base[..., None] + rng.integers(-20, 20, (n, h, w, 3)), 0, 255).astype(np.uint8)
+    else:
+        pages = base.astype(np.uint8)
+    src = _plane(eng, pages)
+    dst = _empty(eng, n, h, w)
+    sig = torch.tensor(sig_est, dtype=torch.float64, device=eng.device)
+    for ww, wh in [(101, 101), (33, 33), (51, 75), (151, 151), (255, 3), (3, 255)]:
+        eng.threshold_mask(src, dst, ww, wh, k=0.34, sigma_dev=sig)
+        got = dst.numpy(np.bool_)
+        for i, s_ in enumerate(sig_est):
+            exp = _threshold_expected(orc, pages[i], s_, ww, wh)
+            assert np.array_equal(got[i], exp), (shape, rgb, ww, wh, s_, int((got[i] != exp).sum()))
+    eng.threshold_mask(src, dst, 75, 75, k=0.2, sigma_dev=None)                           # no sigma array: never blurs
+    got = dst.numpy(np.bool_)
+    for i in range(n):
+        assert np.array_equal(got[i], _threshold_expected(orc, pages[i], None, 75, 75, k=0.2)), (shape, rgb, i)
+
+
+def test_fused_gray_all_colours(eng, orc):
+    """The fused kernel's RGB -> L (two dp4a on the coefficient bytes) on all 2^24 colours: its gray delay-line plane
+    (the threshold workspace) must equal PIL's convert('L')."""
+    import torch
+    allc = np.stack(np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij'), -1)
+    allc = allc.reshape(1, 4096, 4096, 3).astype(np.uint8)
+    src = _plane(eng, allc)
+    dst = _empty(eng, 1, 4096, 4096)
+    eng.threshold_mask(src, dst, 33, 33)
+    torch.cuda.synchronize()
+    ws = eng._ws[('threshold', torch.cuda.current_stream(eng.device).cuda_stream)]
+    off = (-ws.data_ptr()) % 16
+    gray = ws[off:off + 4096 * 4096].reshape(4096, 4096).cpu().numpy()
+    exp = orc.rgb2gray(allc[0])
+    assert np.array_equal(gray, exp), int((gray != exp).sum())
+    assert np.array_equal(dst.numpy(np.bool_)[0], orc.sauvola(exp, 33))
+
+
+@pytest.mark.parametrize('knobs', [{'FUSED_NT': 128, 'FUSED_BANDS': 1}, {'FUSED_NT': 192, 'FUSED_BANDS': 3},
+                                   {'FUSED_NT': 256, 'FUSED_BANDS': 7}, {'FUSED_NT': 128, 'FUSED_BANDS': 40}],
+                         ids=['nt128-1band', 'nt192-3bands', 'nt256-7bands', 'nt128-40bands'])
+def test_threshold_mask_geometries(eng, orc, tuning, knobs):
+    """Every CTA width and several band heights (incl. bands shorter than the window) of the fused kernel, flags, and
+    byte-identical results across launches (the gray delay line is rewritten by overlapping CTAs with equal bytes)."""
+    import torch
+    from archive_pdf_tools_b200 import _lib
+    for k_, v in knobs.items():
+        tuning(k_, v)
+    rng = np.random.default_rng(3)
+    h, w = 500, 1900
+    pages = np.clip(rng.normal(170, 60, (3, h, w, 3)), 0, 255).astype(np.uint8)
+    sig_est = [0.0, 3.0, 5.5]
+    src = _plane(eng, pages); dst = _empty(eng, 3, h, w)
+    sig = torch.tensor(sig_est, dtype=torch.float64, device=eng.device)
+    exp = [_threshold_expected(orc, pages[i], sig_est[i], 101, 101) for i in range(3)]
+    for rep in range(2):
+        eng.threshold_mask(src, dst, 101, 101, sigma_dev=sig)
+        got = dst.numpy(np.bool_)
+        for i in range(3):
+            assert np.array_equal(got[i], exp[i]), (knobs, rep, i, int((got[i] != exp[i]).sum()))
+    pre = rng.random((3, h, w)) < 0.1
+    dst.upload(pre, non_blocking=False)
+    eng.threshold_mask(src, dst, 101, 101, sigma_dev=sig, flags=_lib.SAUVOLA_OR_INTO)
+    got = dst.numpy(np.bool_)
+    for i in range(3):
+        assert np.array_equal(got[i], exp[i] | pre[i])
+    eng.threshold_mask(src, dst, 101, 101, sigma_dev=sig, flags=_lib.SAUVOLA_RAW_INVERTED)
+    got = dst.numpy(np.bool_)
+    for i in range(3):
+        assert np.array_equal(got[i], ~exp[i])
 
 
 @pytest.mark.parametrize('shape', [(33, 25), (100, 77), (330, 255), (64, 64), (7, 5), (600, 450)])
