@@ -107,7 +107,7 @@ def check(status, what=''):
         raise B200MrcError('%s failed (%d): %s' % (what or 'b200mrc call', status, msg.decode() if msg else '?'))
 
 
-TUNING_WORDS = {'single': 1, 'trio': 2, 'tma': 1, 'async': 2, 'legacy': 1, 'generic': 1, 'fused': 0, 'split': 0, 'auto': 0}
+TUNING_WORDS = {'single': 1, 'trio': 2, 'tma': 1, 'async': 2, 'legacy': 1, 'generic': 1, 'fused': 2, 'split': 0, 'auto': 0}
 
 
 def set_tuning(name, value):

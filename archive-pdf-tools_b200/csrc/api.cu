@@ -57,8 +57,8 @@ struct TuneDef { const char *name; int dflt; const char *word1, *word2; };      
 const TuneDef k_tune_defs[T_COUNT] = {
     {"IIRW_MODE", 0, "single", "trio"}, {"IIRW_TPC", 2, nullptr, nullptr}, {"IIRW_FEED", 0, "tma", "async"},
     {"IIRW_PSLEEP", 300, nullptr, nullptr}, {"IIRW_WPC", 2, nullptr, nullptr}, {"FIRW_BAND", 256, nullptr, nullptr},
-    {"FIRW_WPC", 4, nullptr, nullptr}, {"FUSED_NT", 0, nullptr, nullptr}, {"FUSED_BANDS", 0, nullptr, nullptr},
-    {"THRESHOLD_PATH", 0, "legacy", nullptr}, {"OPT_PATH", 0, "generic", nullptr}, {"NOISE_DIRECT", 0, nullptr, nullptr},
+    {"FIRW_WPC", 4, nullptr, nullptr}, {"FUSED_NT", 0, nullptr, nullptr}, {"FUSED_BANDS", 0, nullptr, nullptr}, {"FUSED_DBG", 0, nullptr, nullptr}, {"FUSED_OCC", 0, nullptr, nullptr},
+    {"THRESHOLD_PATH", 0, "legacy", "fused"}, {"OPT_PATH", 0, "generic", nullptr}, {"NOISE_DIRECT", 0, nullptr, nullptr},
     {"RESAMPLE_2PASS", 0, nullptr, nullptr}, {"TILE_H", 32, nullptr, nullptr}, {"DECOMPOSE_GROUPS", 0, nullptr, nullptr},
     {"DECOMPOSE_STREAMS", 0, nullptr, nullptr},
 };
@@ -129,7 +129,10 @@ struct GroupPlan { int groups, per_group, streams; };
 GroupPlan group_plan(int N)
 {
     const int env_groups = tune(T_DECOMPOSE_GROUPS), env_streams = tune(T_DECOMPOSE_STREAMS);
-    int g = env_groups > 0 ? env_groups : (N >= 32 ? 4 : (N >= 8 ? 2 : 1));
+    // measured (profiles/r2_ab_groups.txt): the sweep is row-latency bound, so its time hardly depends on the number of pages;
+    // splitting a 64-page batch multiplies that time and overlap does not win it back.  Groups pay off only when each
+    // of them still fills the machine.
+    int g = env_groups > 0 ? env_groups : (N >= 192 ? 2 : 1);
     if (g > N) g = N;
     GroupPlan gp;
     gp.per_group = (N + g - 1) / g;

@@ -39,9 +39,9 @@ namespace {
 
 constexpr int SK8 = 8;            // columns per thread
 constexpr int NS = 4;             // TMA stages (source rows in flight)
-constexpr int EB = 128;           // bias of prefix entry indices (window half-width <= 128)
 constexpr int MAXR = 2;           // largest blur radius produced in-kernel
-constexpr unsigned FULLW = 0xffffffffu;
+constexpr int STAGE_PAD = 16;     // bytes in front of / behind a staged row (neighbour reads of the CTA's edge lanes)
+constexpr unsigned FULLM = 0xffffffffu;
 
 struct FusedParams {
     const uint8_t *src; int64_t src_pitch, src_stride;          // page image, C = 1 or 3 (template)
@@ -51,25 +51,33 @@ struct FusedParams {
     int W, H;
     int ww, wh, l, r, o, u;
     int n_strips, strip_w, ext_left, n_bands, band_h;
-    int sps;                                                    // prefix plane stride (entries per residue row)
+    int sps, eb;                                                // prefix plane stride (entries per residue row); bias of the entry indices
     double km1, k2;
     int flags;
     int out8;                                                   // out rows allow 8-byte stores
+    int dbg;                                                    // FUSED_DBG: timing experiments only (results wrong): 1 no test, 2 no blur, 4 no scan/publish, 8 no slide, 16 no row barrier
+    // byte offsets, inside one prefix buffer and relative to the thread's slot, of the entries a thread publishes
+    // (st) and of the two window-edge entries of each of its 8 pixels (hi, lo): uniform values, so the shared-memory
+    // accesses take them from the uniform register file
+    int bo_st[SK8], bo_hi[SK8], bo_lo[SK8];
 };
 
 // smem carve-up (bytes), nt = threads per CTA
 struct FusedSmem {
-    int off_wt, off_my, off_v, off_p, off_stage, total;
-    __host__ __device__ FusedSmem(int nt, int C)
+    int off_rowbar, off_wt, off_my, off_mx, off_p, off_stage, stage_stride, pbuf_bytes, total;
+    __host__ __device__ FusedSmem(int nt, int C, int eb)
     {
         const int ncols = nt * SK8;
-        const int sps = (ncols + 2 * EB + 8 + 7) / 8;
-        off_wt = 256;                                   // [2][8] uint2 (mbarriers at 0, weights at 64)
-        off_my = off_wt + 2 * 8 * 8;                    // [256] uint2
-        off_v = off_my + 256 * 8;                       // [2][ncols + 8] float
-        off_p = (off_v + 2 * (ncols + 8) * 4 + 15) & ~15;   // [2][8][sps] uint2
-        off_stage = (off_p + 2 * 8 * sps * 8 + 127) & ~127; // [NS][ncols * C]
-        total = off_stage + NS * ncols * C;
+        const int sps = (ncols + 2 * eb + 8 + 7) / 8;
+        off_rowbar = 32;                                // TMA mbarriers at 0 (NS x 8), weights at 64
+        off_wt = 256;                                   // [2][8] uint2 warp totals
+        off_my = off_wt + 2 * 8 * 8;                    // [256] uint2: magic of n = ww * ny
+        off_mx = off_my + 256 * 8;                      // [256] uint2: magic of n = nx * wh
+        off_p = off_mx + 256 * 8;                       // [3][8][sps] uint2 prefix of the column sums
+        pbuf_bytes = 8 * sps * 8;
+        off_stage = (off_p + 3 * pbuf_bytes + 127) & ~127;      // [NS][stage_stride]
+        stage_stride = (ncols * C + 2 * STAGE_PAD + 15) & ~15;
+        total = off_stage + NS * stage_stride;
     }
 };
 
@@ -89,26 +97,42 @@ __device__ __forceinline__ void scan_up2f(uint32_t &a, uint32_t &b, int d)
         : "+r"(a), "+r"(b) : "r"(d));
 }
 
-template <int V> struct IC { static constexpr int value = V; };
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // CS = channels of the source plane, R = blur radius produced here, PRODUCE = gray rows are produced (and written to the
 // delay line); otherwise the source IS the gray plane and is read directly.
+//
+// One iteration y of the row loop (every thread, 8 columns):
+//   B  scan of the column sums of row y+1 (thread total -> warp shuffle scan -> warp total to smem); ARRIVE on the row barrier
+//   A  source row y+2+u+R from its TMA stage -> gray -> (R > 0) blur: the vertical pass runs on a (2R+1)-row register window
+//      for the thread's 8 columns plus R neighbour columns per side (their gray bytes come from the adjacent lanes by
+//      shuffle; a warp's edge lanes convert them from the stage), so the horizontal pass needs nobody else -> gray row
+//      rc = y+2+u, written to the delay line
+//   D  test of row y-1 against the prefix published two iterations ago (sP is a ring of three buffers)
+//   -- WAIT on the row barrier: everything between ARRIVE and WAIT is independent of the other warps, so a warp only
+//      stalls here if it runs most of an iteration ahead of the slowest one
+//   C  CTA-wide prefix of row y+1 (base = totals of the lower warps) -> third buffer
+//   E  slide the window: + gray row rc, - gray row y+2-o (delay line)
 template <int CS, int R, bool PRODUCE>
 __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem, const uint8_t *src, int64_t src_pitch,
                                             uint8_t *gray, uint8_t *out, const double *sw)
 {
     static_assert(PRODUCE || (CS == 1 && R == 0), "direct mode reads a gray plane");
+    constexpr int NE = SK8 + 2 * R;                  // columns of the vertical pass
     const int nt = blockDim.x, ncols = nt * SK8;
-    const FusedSmem L(nt, CS);                       // stage region is sized by the launcher for the kernel's C >= CS
+    const FusedSmem L(nt, CS, p.eb);                 // offsets up to the stage region do not depend on the channel count
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *rowbar = reinterpret_cast<uint64_t *>(smem + L.off_rowbar);
     uint2 *sWT = reinterpret_cast<uint2 *>(smem + L.off_wt);
     const uint2 *sMY = reinterpret_cast<const uint2 *>(smem + L.off_my);
-    float *sV = reinterpret_cast<float *>(smem + L.off_v);
-    uint2 *sP = reinterpret_cast<uint2 *>(smem + L.off_p);
-    uint8_t *stage = smem + L.off_stage;
-    const int sps = p.sps, pbuf = 8 * sps, vbuf = ncols + 8;
+    const uint2 *sMX = reinterpret_cast<const uint2 *>(smem + L.off_mx);
+    uint8_t *stage = smem + L.off_stage + STAGE_PAD;
+    const int stage_stride = (ncols * CS + 2 * STAGE_PAD + 15) & ~15;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
     const int W = p.W, H = p.H;
     const int sx0 = strip * p.strip_w;
@@ -126,29 +150,32 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
         const int v = W - (gx + 4 * h);              // valid columns from this word on
         lmask[h] = (!lok || v <= 0) ? 0u : (v >= 4 ? 0xffffffffu : (1u << (8 * v)) - 1u);
     }
-    // window widths: interior threads have ww for all 8 pixels
-    const bool nx_uniform = gx - p.l + 1 >= 0 && gx + 7 + p.r + 1 <= W;
-    const bool blur_edge = R > 0 && (gx - R < 0 || gx + 7 + R >= W);
+    const bool nx_uniform = gx - p.l + 1 >= 0 && gx + 7 + p.r + 1 <= W;     // window width ww for all 8 pixels
+    const bool edge_l = R > 0 && gx == 0;                                     // blur taps left of the page: scipy 'reflect'
+    const bool edge_r = R > 0 && lok && gx + 7 + R >= W;                      // blur taps right of the page
 
     // ---- TMA feed of the source rows (one elected thread)
     const int cx0 = max(ex0, 0);
     const uint32_t copy_bytes = (uint32_t)(min((ex0 + ncols) * CS, ((W * CS + 15) & ~15)) - cx0 * CS);
     const int dst_off = (cx0 - ex0) * CS;
     const uint8_t *src_col = src + (int64_t)cx0 * CS;
-    const int stage_bytes = ncols * CS;
     const int g0 = max(0, by0 - p.o + 1);            // first gray row this band needs
     const int y_start = g0 - 2 - p.u - 2 * R;        // iteration y consumes source row y + 2 + u + R and completes gray row y + 2 + u
-    const int rs_first = g0 - R, rs_last = by1 + 1 + p.u + R;
+    const int n_it = by1 - y_start + 1;              // iterations y_start .. by1 (the test runs one row behind)
+    const int rs_first = g0 - R, rs_last = rs_first + n_it - 1;
     auto issue_row = [&](int rs, int s) {
         mbar_expect_tx(&mbar[s], copy_bytes);
-        tma_load(stage + s * stage_bytes + dst_off, src_col + (int64_t)reflect_idx(rs, H) * src_pitch, copy_bytes, &mbar[s]);
+        tma_load(stage + s * stage_stride + dst_off, src_col + (int64_t)reflect_idx(rs, H) * src_pitch, copy_bytes, &mbar[s]);
     };
     if (tid == 0) {
+        mbar_init(rowbar, nt >> 5);
+        fence_mbar_init();
 #pragma unroll
         for (int s = 0; s < NS; s++)
             if (rs_first + s <= rs_last) issue_row(rs_first + s, s);
     }
-    if (tid < 2) sP[tid * pbuf + (EB & 7) * sps + (EB >> 3)] = make_uint2(0u, 0u);      // prefix entry of "no columns"
+    uint8_t *pb = smem + L.off_p + tid * 8;          // this thread's slot in prefix buffer 0
+    if (tid < 3) *reinterpret_cast<uint2 *>(smem + L.off_p + tid * L.pbuf_bytes + ((p.eb & 7) * p.sps + (p.eb >> 3)) * 8) = make_uint2(0u, 0u);   // prefix of "no columns"
 
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;
     if constexpr (R > 0) { w0 = sw[0]; w1 = sw[1]; if constexpr (R > 1) w2 = sw[2]; }
@@ -156,9 +183,9 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     uint32_t cs[SK8], cq[SK8];
 #pragma unroll
     for (int k = 0; k < SK8; k++) { cs[k] = 0; cq[k] = 0; }
-    uint32_t win[2 * R + 1][2];
+    uint32_t win[2 * R + 1][3];                      // per row: neighbour bytes (left | right), own 8 gray bytes
 #pragma unroll
-    for (int j = 0; j < 2 * R + 1; j++) { win[j][0] = 0; win[j][1] = 0; }
+    for (int j = 0; j < 2 * R + 1; j++) { win[j][0] = 0; win[j][1] = 0; win[j][2] = 0; }
 
     // delay-line reads (current row / leaving row), two iterations ahead
     const uint8_t *dl = PRODUCE ? gray : src;
@@ -172,96 +199,108 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     };
     uint32_t cA[2] = {0, 0}, lA[2] = {0, 0}, cB[2] = {0, 0}, lB[2] = {0, 0};
 
-    const int it_main = (by0 - 1) - y_start;         // first main iteration
+    const int it_main = (by0 - 1) - y_start;         // first main iteration (>= 2)
     int slot = 0, par = 0;
+    int o_test = 0, o_mid = L.pbuf_bytes, o_pub = 2 * L.pbuf_bytes;      // prefix ring: L(y-1), L(y), L(y+1)
     int ny_cached = -1;
     uint32_t magicM = 0, magicS = 0;
-    uint8_t *orow = out + (int64_t)by0 * p.out_pitch + gx;
+    uint8_t *orow = out + (int64_t)by0 * p.out_pitch + gx;                // next mask row to write
     uint8_t *grow = PRODUCE ? gray + (int64_t)g0 * p.gray_pitch + gx : nullptr;   // next delay-line row to write (row rc)
 
-    auto step = [&](auto PARC, const int y, const int it) {
-        constexpr int PB = decltype(PARC)::value;
+    __syncthreads();                                 // barrier init + prefix zero entries visible
+
+    for (int it = 0; it < n_it; it++) {
+        const int y = y_start + it;
         const bool main = it >= it_main;
-        // ================= part 1: source row -> gray words -> vertical pass; scan of the column sums
-        mbar_wait(&mbar[slot], (uint32_t)par);
-        uint32_t gw[2];
-        {
-            const uint8_t *sp = stage + slot * stage_bytes + i0 * CS;
-            if (CS == 3) {
-                const uint2 a = *reinterpret_cast<const uint2 *>(sp), b = *reinterpret_cast<const uint2 *>(sp + 8),
-                            c = *reinterpret_cast<const uint2 *>(sp + 16);
-                const uint32_t wv[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                constexpr uint32_t KH0 = 76u | (150u << 8) | (29u << 16), KL0 = 139u | (70u << 8) | (47u << 16);
-                constexpr uint32_t KH1 = KH0 << 8, KL1 = KL0 << 8;
-                uint32_t tv[8];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t x0 = wv[3 * h], x1 = wv[3 * h + 1], x2 = wv[3 * h + 2];
-                    const uint32_t p1 = __byte_perm(x0, x1, 0x0543), p2 = __byte_perm(x1, x2, 0x0432);
-                    tv[4 * h + 0] = __dp4a(x0, KH0, 0u) * 256u + __dp4a(x0, KL0, 0x8000u);
-                    tv[4 * h + 1] = __dp4a(p1, KH0, 0u) * 256u + __dp4a(p1, KL0, 0x8000u);
-                    tv[4 * h + 2] = __dp4a(p2, KH0, 0u) * 256u + __dp4a(p2, KL0, 0x8000u);
-                    tv[4 * h + 3] = __dp4a(x2, KH1, 0u) * 256u + __dp4a(x2, KL1, 0x8000u);
-                    // L = bits 16..23 of each total
-                    gw[h] = __byte_perm(__byte_perm(tv[4 * h], tv[4 * h + 1], 0x0062), __byte_perm(tv[4 * h + 2], tv[4 * h + 3], 0x0062), 0x5410);
-                }
-            } else {
-                const uint2 a = *reinterpret_cast<const uint2 *>(sp);
-                gw[0] = a.x; gw[1] = a.y;
-            }
-        }
-        if constexpr (R > 0) {
-#pragma unroll
-            for (int j = 0; j < 2 * R; j++) { win[j][0] = win[j + 1][0]; win[j][1] = win[j + 1][1]; }
-            win[2 * R][0] = gw[0]; win[2 * R][1] = gw[1];
-            float v[SK8];
-#pragma unroll
-            for (int k = 0; k < SK8; k++) {
-                const int h = k >> 2, b = k & 3;
-                double acc = __dmul_rn(u2d(byte_of(win[R][h], b)), w0);
-                if constexpr (R > 1) acc = __dadd_rn(acc, __dmul_rn(u2d(byte_of(win[0][h], b) + byte_of(win[2 * R][h], b)), w2));
-                acc = __dadd_rn(acc, __dmul_rn(u2d(byte_of(win[R - 1][h], b) + byte_of(win[R + 1][h], b)), w1));
-                v[k] = __double2float_rn(acc);
-            }
-            float *vd = sV + PB * vbuf + 4 + i0;
-            *reinterpret_cast<float4 *>(vd) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(vd + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        uint32_t ps[SK8], pq[SK8], bs = 0, bq = 0;
-        if (main) {
-            ps[0] = cs[0]; pq[0] = cq[0];
-#pragma unroll
-            for (int k = 1; k < SK8; k++) { ps[k] = ps[k - 1] + cs[k]; pq[k] = pq[k - 1] + cq[k]; }
-            uint32_t ws = ps[SK8 - 1], wq = pq[SK8 - 1];
+        // ================= B: scan of the column sums of row y+1
+        uint32_t bs = 0, bq = 0;
+        if (main && !(p.dbg & 4)) {
+            const uint32_t ts = ((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]));
+            const uint32_t tq = ((cq[0] + cq[1]) + (cq[2] + cq[3])) + ((cq[4] + cq[5]) + (cq[6] + cq[7]));
+            uint32_t ws = ts, wq = tq;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) scan_up2f(ws, wq, d);
-            if (lane == 31) sWT[PB * 8 + warp] = make_uint2(ws, wq);
-            bs = ws - ps[SK8 - 1]; bq = wq - pq[SK8 - 1];       // exclusive within the warp
+            if (lane == 31) sWT[(it & 1) * 8 + warp] = make_uint2(ws, wq);
+            bs = ws - ts; bq = wq - tq;              // exclusive within the warp
         }
-        __syncthreads();
-        if (tid == 0 && y + 2 + p.u + R + NS <= rs_last) issue_row(y + 2 + p.u + R + NS, slot);   // every thread has read this stage
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 16)) mbar_arrive_cta(rowbar);
 
-        // ================= part 2: horizontal pass -> gray row rc; publish the prefix; test row y; slide the window
-        const int rc = y + 2 + p.u;
-        uint32_t G[2];
-        if constexpr (R > 0) {
-            const float *vs = sV + PB * vbuf + 4;
-            double ext[SK8 + 2 * R];
-            if (!blur_edge) {
-                const float4 a = *reinterpret_cast<const float4 *>(vs + i0), b = *reinterpret_cast<const float4 *>(vs + i0 + 4);
-                ext[R + 0] = (double)a.x; ext[R + 1] = (double)a.y; ext[R + 2] = (double)a.z; ext[R + 3] = (double)a.w;
-                ext[R + 4] = (double)b.x; ext[R + 5] = (double)b.y; ext[R + 6] = (double)b.z; ext[R + 7] = (double)b.w;
+        // ================= A: source row -> gray row rc
+        mbar_wait(&mbar[slot], (uint32_t)par);
+        uint32_t gw[2];
+        const uint8_t *sp = stage + slot * stage_stride + i0 * CS;
+        if (CS == 3) {
+            const uint2 a = *reinterpret_cast<const uint2 *>(sp), b = *reinterpret_cast<const uint2 *>(sp + 8),
+                        c = *reinterpret_cast<const uint2 *>(sp + 16);
+            const uint32_t wv[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            constexpr uint32_t KH0 = 76u | (150u << 8) | (29u << 16), KL0 = 139u | (70u << 8) | (47u << 16);
+            constexpr uint32_t KH1 = KH0 << 8, KL1 = KL0 << 8;
 #pragma unroll
-                for (int j = 0; j < R; j++) { ext[j] = (double)vs[i0 - R + j]; ext[R + SK8 + j] = (double)vs[i0 + SK8 + j]; }
-            } else {
-                // columns outside the page are scipy-reflected (vertical-pass results mirror with their columns)
-#pragma unroll
-                for (int j = 0; j < SK8 + 2 * R; j++) {
-                    int li = reflect_idx(gx - R + j, W) - ex0;
-                    li = min(max(li, -4), ncols + 3);
-                    ext[j] = (double)vs[li];
-                }
+            for (int h = 0; h < 2; h++) {
+                const uint32_t x0 = wv[3 * h], x1 = wv[3 * h + 1], x2 = wv[3 * h + 2];
+                const uint32_t p1 = __byte_perm(x0, x1, 0x0543), p2 = __byte_perm(x1, x2, 0x0432);
+                const uint32_t t0 = __dp4a(x0, KH0, 0u) * 256u + __dp4a(x0, KL0, 0x8000u);
+                const uint32_t t1 = __dp4a(p1, KH0, 0u) * 256u + __dp4a(p1, KL0, 0x8000u);
+                const uint32_t t2 = __dp4a(p2, KH0, 0u) * 256u + __dp4a(p2, KL0, 0x8000u);
+                const uint32_t t3 = __dp4a(x2, KH1, 0u) * 256u + __dp4a(x2, KL1, 0x8000u);
+                gw[h] = __byte_perm(__byte_perm(t0, t1, 0x0062), __byte_perm(t2, t3, 0x0062), 0x5410);   // L = bits 16..23
             }
+        } else {
+            const uint2 a = *reinterpret_cast<const uint2 *>(sp);
+            gw[0] = a.x; gw[1] = a.y;
+        }
+        uint32_t G[2];
+        if (R > 0 && (p.dbg & 2)) { G[0] = gw[0]; G[1] = gw[1]; } else
+        if constexpr (R > 0) {
+            // neighbour columns: R to the left (from lane - 1), R to the right (from lane + 1)
+            uint32_t left = __shfl_up_sync(FULLM, gw[1], 1), right = __shfl_down_sync(FULLM, gw[0], 1);
+            if (lane == 0 || lane == 31) {
+                // the neighbour lane belongs to another warp: convert its pixels from the stage
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const uint8_t *q = lane == 0 ? sp - (R - j) * CS : sp + (SK8 + j) * CS;
+                    const uint32_t g = CS == 3 ? luma_l24(q[0], q[1], q[2]) : (uint32_t)q[0];
+                    acc |= g << (8 * (lane == 0 ? 4 - R + j : j));
+                }
+                if (lane == 0) left = acc; else right = acc;
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * R; j++) { win[j][0] = win[j + 1][0]; win[j][1] = win[j + 1][1]; win[j][2] = win[j + 1][2]; }
+            win[2 * R][0] = R == 1 ? __byte_perm(left, right, 0x0043) : __byte_perm(left, right, 0x5432);
+            win[2 * R][1] = gw[0]; win[2 * R][2] = gw[1];
+            // column e of window row j: e < R left neighbours, e >= R + 8 right neighbours
+            auto colv = [&](const int j, const int e) -> uint32_t {
+                if (e < R) return byte_of(win[j][0], e);
+                if (e >= R + SK8) return byte_of(win[j][0], e - SK8);
+                return byte_of(win[j][1 + ((e - R) >> 2)], (e - R) & 3);
+            };
+            float vf[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                double acc = __dmul_rn(u2d(colv(R, e)), w0);
+                if constexpr (R > 1) acc = __dadd_rn(acc, __dmul_rn(u2d(colv(0, e) + colv(2 * R, e)), w2));
+                acc = __dadd_rn(acc, __dmul_rn(u2d(colv(R - 1, e) + colv(R + 1, e)), w1));
+                vf[e] = __double2float_rn(acc);
+            }
+            // columns outside the page are scipy-reflected; vertical-pass results mirror with their columns
+            if (edge_l) {
+#pragma unroll
+                for (int j = 0; j < R; j++) vf[R - 1 - j] = vf[R + j];
+            }
+            if (edge_r) {
+                float tmp[NE];
+#pragma unroll
+                for (int e = 0; e < NE; e++) tmp[e] = vf[e];
+                const int kk = 2 * W - 1 - 2 * (gx - R);         // column c = gx - R + e mirrors to index kk - e
+#pragma unroll
+                for (int e = 0; e < NE; e++)
+                    if (gx - R + e >= W) vf[e] = tmp[min(max(kk - e, 0), NE - 1)];
+            }
+            double ext[NE];
+#pragma unroll
+            for (int e = 0; e < NE; e++) ext[e] = (double)vf[e];
             uint32_t ob[SK8];
 #pragma unroll
             for (int k = 0; k < SK8; k++) {
@@ -275,6 +314,7 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
         } else {
             G[0] = gw[0]; G[1] = gw[1];
         }
+        const int rc = y + 2 + p.u;
         const bool rc_ok = rc >= g0 && rc < H;
         if (PRODUCE) {
             if (rc >= g0) {
@@ -285,98 +325,113 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
         if (!rc_ok) { G[0] = 0; G[1] = 0; }
         G[0] &= lmask[0]; G[1] &= lmask[1];
 
-        if (main) {
-            // ---- CTA-wide prefix of the column sums of row y+1 -> the other buffer (read in the next iteration)
-            {
-                uint32_t as = bs, aq = bq;
-                const uint2 *T = sWT + PB * 8;
-                for (int w2i = 0; w2i < warp; w2i++) { const uint2 t = T[w2i]; as += t.x; aq += t.y; }
-                uint2 *P = sP + (PB ^ 1) * pbuf + (EB >> 3) + tid;
-#pragma unroll
-                for (int k = 0; k < SK8; k++) P[((k + 1) & 7) * sps + ((k + 1) >> 3)] = make_uint2(as + ps[k], aq + pq[k]);
-            }
-            // ---- test of row y
-            if (y >= by0) {
-                if (is_out) {
-                    const uint2 *P = sP + PB * pbuf + tid;
-                    const int ny = min(H, y + p.u + 1) - max(0, y - p.o + 1);
-                    if (ny != ny_cached) { const uint2 m = sMY[ny]; magicM = m.x; magicS = m.y; ny_cached = ny; }
-                    uint32_t S[SK8], Q[SK8];
-#pragma unroll
-                    for (int k = 0; k < SK8; k++) {
-                        const int qh = EB + p.r + 1 + k, ql = EB - p.l + 1 + k;
-                        const uint2 hi = P[(qh & 7) * sps + (qh >> 3)];
-                        const uint2 lo = P[(ql & 7) * sps + (ql >> 3)];
-                        S[k] = hi.x - lo.x; Q[k] = hi.y - lo.y;
-                    }
-                    uint32_t bits[2] = {0, 0};
-                    if (nx_uniform && magicM != 0u) {
-#pragma unroll
-                        for (int k = 0; k < SK8; k++) {
-                            const uint32_t m = __umulhi(S[k], magicM) >> magicS, q = __umulhi(Q[k], magicM) >> magicS;
-                            const double md = u2d(m), vd = u2d(q - m * m), pd = u2d(byte_of(cA[k >> 2], k & 3));
-                            const double mm = __dmul_rn(md, md);
-                            const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
-                            const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
-                            const double lhs = __dmul_rn(t, t);
-                            const uint32_t fg = ((t <= 0.0) || (lhs <= rhs)) ? 1u : 0u;
-                            bits[k >> 2] |= fg << (8 * (k & 3));
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < SK8; k++) {
-                            const int x = gx + k;
-                            const int nx = (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0;
-                            const int n = nx * ny;
-                            if (n > 0) {
-                                // floor((a + 0.5) * (1/n)) == a / n exactly (sauvola.cu)
-                                const double rn = 1.0 / (double)n;
-                                const double md = floor(__dmul_rn(__dadd_rn((double)S[k], 0.5), rn));
-                                const double qd = floor(__dmul_rn(__dadd_rn((double)Q[k], 0.5), rn));
-                                const double mm = __dmul_rn(md, md);
-                                const double vd = __dadd_rn(qd, -mm);
-                                const double pd = (double)byte_of(cA[k >> 2], k & 3);
-                                const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
-                                const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
-                                const double lhs = __dmul_rn(t, t);
-                                const uint32_t fg = ((t <= 0.0) || (lhs <= rhs)) ? 1u : 0u;
-                                bits[k >> 2] |= fg << (8 * (k & 3));
-                            }
-                        }
-                    }
-                    if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) { bits[0] ^= 0x01010101u; bits[1] ^= 0x01010101u; }
-                    if (gx + 7 < W) {
-                        if (p.out8) {
-                            uint2 *o64 = reinterpret_cast<uint2 *>(orow);
-                            if (p.flags & B200MRC_SAUVOLA_OR_INTO) { const uint2 old = *o64; bits[0] |= old.x; bits[1] |= old.y; }
-                            *o64 = make_uint2(bits[0], bits[1]);
-                        } else {
-                            uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
-                            if (p.flags & B200MRC_SAUVOLA_OR_INTO) { bits[0] |= o32[0]; bits[1] |= o32[1]; }
-                            o32[0] = bits[0]; o32[1] = bits[1];
-                        }
-                    } else {
-                        for (int k = 0; k < SK8 && gx + k < W; k++) {
-                            uint8_t b = (uint8_t)((bits[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                            if (p.flags & B200MRC_SAUVOLA_OR_INTO) b |= orow[k];
-                            orow[k] = b;
-                        }
-                    }
-                }
-                orow += p.out_pitch;
-            }
-            // ---- slide: row y+2's window = row y+1's + gray row rc - gray row y+2-o
-            {
-                const uint32_t l0 = lA[0] & lmask[0], l1 = lA[1] & lmask[1];
+        // ================= D: test of row y-1 (prefix published two iterations ago, pixels from the delay line)
+        if (main && y - 1 >= by0) {
+            if (is_out && !(p.dbg & 1)) {
+                const int yt = y - 1;
+                const uint8_t *P = pb + o_test;
+                const int ny = min(H, yt + p.u + 1) - max(0, yt - p.o + 1);
+                if (ny != ny_cached) { const uint2 m = sMY[ny]; magicM = m.x; magicS = m.y; ny_cached = ny; }
+                uint32_t S[SK8], Q[SK8];
 #pragma unroll
                 for (int k = 0; k < SK8; k++) {
-                    const uint32_t a = byte_of(G[k >> 2], k & 3), b = byte_of(k < 4 ? l0 : l1, k & 3);
-                    cs[k] += a - b;
-                    cq[k] += a * a - b * b;
+                    const uint2 hi = *reinterpret_cast<const uint2 *>(P + p.bo_hi[k]);
+                    const uint2 lo = *reinterpret_cast<const uint2 *>(P + p.bo_lo[k]);
+                    S[k] = hi.x - lo.x; Q[k] = hi.y - lo.y;
+                }
+                auto test_fast = [&](const int k, const uint32_t M, const uint32_t sh) -> uint32_t {
+                    const uint32_t m = __umulhi(S[k], M) >> sh, q = __umulhi(Q[k], M) >> sh;
+                    const double md = u2d(m), vd = u2d(q - m * m), pd = u2d(byte_of(cA[k >> 2], k & 3));
+                    const double mm = __dmul_rn(md, md);
+                    const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
+                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
+                    const double lhs = __dmul_rn(t, t);
+                    return (uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs);
+                };
+                auto test_slow = [&](const int k, const int n) -> uint32_t {
+                    // floor((a + 0.5) * (1/n)) == a / n exactly (sauvola.cu)
+                    const double rn = 1.0 / (double)n;
+                    const double md = floor(__dmul_rn(__dadd_rn((double)S[k], 0.5), rn));
+                    const double qd = floor(__dmul_rn(__dadd_rn((double)Q[k], 0.5), rn));
+                    const double mm = __dmul_rn(md, md);
+                    const double vd = __dadd_rn(qd, -mm);
+                    const double pd = (double)byte_of(cA[k >> 2], k & 3);
+                    const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
+                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
+                    const double lhs = __dmul_rn(t, t);
+                    return (uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs);
+                };
+                uint32_t bits[2] = {0, 0};
+                if (nx_uniform && magicM != 0u) {
+                    // interior columns: one window area per row
+#pragma unroll
+                    for (int k = 0; k < SK8; k++) bits[k >> 2] |= test_fast(k, magicM, magicS) << (8 * (k & 3));
+                } else {
+                    // columns whose window is clamped by the page: per-pixel area; interior rows still divide by table
+#pragma unroll
+                    for (int k = 0; k < SK8; k++) {
+                        const int x = gx + k;
+                        const int nx = (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0;
+                        if (nx > 0) {
+                            const uint2 mg = (ny == p.wh) ? sMX[nx] : make_uint2(0u, 0u);
+                            const uint32_t fg = mg.x ? test_fast(k, mg.x, mg.y) : test_slow(k, nx * ny);
+                            bits[k >> 2] |= fg << (8 * (k & 3));
+                        }
+                    }
+                }
+                if (p.flags & B200MRC_SAUVOLA_RAW_INVERTED) { bits[0] ^= 0x01010101u; bits[1] ^= 0x01010101u; }
+                if (gx + 7 < W) {
+                    if (p.out8) {
+                        uint2 *o64 = reinterpret_cast<uint2 *>(orow);
+                        if (p.flags & B200MRC_SAUVOLA_OR_INTO) { const uint2 old = *o64; bits[0] |= old.x; bits[1] |= old.y; }
+                        *o64 = make_uint2(bits[0], bits[1]);
+                    } else {
+                        uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
+                        if (p.flags & B200MRC_SAUVOLA_OR_INTO) { bits[0] |= o32[0]; bits[1] |= o32[1]; }
+                        o32[0] = bits[0]; o32[1] = bits[1];
+                    }
+                } else {
+                    for (int k = 0; k < SK8 && gx + k < W; k++) {
+                        uint8_t b = (uint8_t)((bits[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                        if (p.flags & B200MRC_SAUVOLA_OR_INTO) b |= orow[k];
+                        orow[k] = b;
+                    }
                 }
             }
+            orow += p.out_pitch;
+        }
+
+        // ================= WAIT: every warp has published its total of row y+1 (and is done with the previous stage)
+        if (!(p.dbg & 16)) mbar_wait(rowbar, (uint32_t)(it & 1)); else __syncthreads();
+        if (tid == 0 && it > 0) {
+            const int rs = rs_first + (it - 1) + NS;                 // refill the stage every thread read in iteration it-1
+            if (rs <= rs_last) issue_row(rs, slot == 0 ? NS - 1 : slot - 1);
+        }
+        if (main && (p.dbg & 4)) { const int t_ = o_test; o_test = o_mid; o_mid = o_pub; o_pub = t_; }
+        if (main && (p.dbg & 8)) { cA[0] = cB[0]; cA[1] = cB[1]; cs[0] += G[0]; }
+        if (main && !(p.dbg & 12)) {
+            // ================= C: CTA-wide prefix of the column sums of row y+1 -> ring buffer o_pub
+            uint32_t as = bs, aq = bq;
+            const uint2 *T = sWT + (it & 1) * 8;
+            for (int w2i = 0; w2i < warp; w2i++) { const uint2 t = T[w2i]; as += t.x; aq += t.y; }
+            uint8_t *P = pb + o_pub;
+#pragma unroll
+            for (int k = 0; k < SK8; k++) {
+                as += cs[k]; aq += cq[k];
+                *reinterpret_cast<uint2 *>(P + p.bo_st[k]) = make_uint2(as, aq);
+            }
+            // ================= E: slide: row y+2's window = row y+1's + gray row rc - gray row y+2-o
+            const uint32_t l0 = lA[0] & lmask[0], l1 = lA[1] & lmask[1];
+#pragma unroll
+            for (int k = 0; k < SK8; k++) {
+                const uint32_t a = byte_of(G[k >> 2], k & 3), b = byte_of(k < 4 ? l0 : l1, k & 3);
+                cs[k] += a - b;
+                cq[k] += a * a - b * b;
+            }
             cA[0] = cB[0]; cA[1] = cB[1]; lA[0] = lB[0]; lA[1] = lB[1];
-            if (y + 2 < by1) { load_row(y + 2, cB); load_row(y + 4 - p.o, lB); }
+            if (y + 1 < by1) load_row(y + 1, cB);
+            if (y + 2 < by1) load_row(y + 4 - p.o, lB);
+            const int t_ = o_test; o_test = o_mid; o_mid = o_pub; o_pub = t_;
         } else {
             // warm-up: gray row rc joins the window of the band's first row
 #pragma unroll
@@ -385,26 +440,17 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                 cs[k] += a; cq[k] += a * a;
             }
             if (it + 1 == it_main) {
-                // the delay line now holds every row the first two main iterations read back
+                // the delay line now holds every row the first two main iterations subtract
                 load_row(by0 + 1 - p.o, lA);
-                load_row(by0, cB); load_row(by0 + 2 - p.o, lB);
+                load_row(by0 + 2 - p.o, lB);
             }
         }
         if (++slot == NS) { slot = 0; par ^= 1; }
-    };
-
-    __syncthreads();                                   // mbarrier init + prefix zero entry visible
-    const int n_it = by1 - y_start;                    // iterations y_start .. by1-1
-    if (it_main == 0) {                                // no warm-up iteration (cannot happen for window >= 3; kept for safety)
-        load_row(by0 + 1 - p.o, lA); load_row(by0, cB); load_row(by0 + 2 - p.o, lB);
     }
-    int it = 0;
-    for (; it + 1 < n_it; it += 2) { step(IC<0>(), y_start + it, it); step(IC<1>(), y_start + it + 1, it + 1); }
-    if (it < n_it) step(IC<0>(), y_start + it, it);
 }
 
-template <int C>
-__global__ void __launch_bounds__(256, 2) k_sauvola_fused(const FusedParams p)
+template <int C, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_sauvola_fused(const FusedParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
@@ -412,7 +458,7 @@ __global__ void __launch_bounds__(256, 2) k_sauvola_fused(const FusedParams p)
     double *sphi = sw + 4;                                       // 5 scratch
     const int page = blockIdx.y;
     const int tid = threadIdx.x;
-    const FusedSmem L(blockDim.x, C);
+    const FusedSmem L(blockDim.x, C, p.eb);
 
     double sigma;
     const int radius = blur_radius_of(p.sigma, page, sigma);
@@ -433,6 +479,17 @@ __global__ void __launch_bounds__(256, 2) k_sauvola_fused(const FusedParams p)
                 e.y = (uint32_t)sh;
             }
             my[ny] = e;
+        }
+        uint2 *mx = reinterpret_cast<uint2 *>(smem + L.off_mx);
+        for (int nx = tid; nx < 256; nx += blockDim.x) {
+            const int n = nx * p.wh;
+            uint2 e = make_uint2(0u, 0u);
+            if (fast_div_ok(n)) {
+                const int sh = 31 - __clz(n - 1);
+                e.x = (uint32_t)(((1ull << (32 + sh)) + (unsigned long long)n - 1ull) / (unsigned long long)n);
+                e.y = (uint32_t)sh;
+            }
+            mx[nx] = e;
         }
     }
     if (radius >= 1 && radius <= MAXR) blur_weights_cta(radius, sigma, sw, sphi);
@@ -508,27 +565,29 @@ int launch_sauvola_fused(const uint8_t *src, int64_t src_pitch, int64_t src_stri
     const int sw_max = (ncols - p.ext_left - right) / 16 * 16;
     p.n_strips = cdiv(W, sw_max);
     p.strip_w = (cdiv(W, p.n_strips) + 15) / 16 * 16;
-    p.sps = (ncols + 2 * EB + 8 + 7) / 8;
+    p.eb = (p.l + 7) / 8 * 8;                                     // entry index of column c is c + eb >= 1
+    p.sps = (ncols + 2 * p.eb + 8 + 7) / 8;
+    for (int k = 0; k < SK8; k++) {
+        auto bo = [&](int q) { return ((q & 7) * p.sps + (q >> 3)) * 8; };
+        p.bo_st[k] = bo(p.eb + k + 1); p.bo_hi[k] = bo(p.eb + p.r + 1 + k); p.bo_lo[k] = bo(p.eb - p.l + 1 + k);
+    }
     p.km1 = k - 1.0;
     p.k2 = k * k / Rr / Rr;                                       // sauvola.pyx:60
     p.flags = flags;
+    p.dbg = tune(T_FUSED_DBG);
     p.out8 = !(((uintptr_t)out & 7) || (out_pitch & 7) || (out_stride & 7));
 
-    const FusedSmem L(nt, C);
-    const void *kern = C == 3 ? (const void *)k_sauvola_fused<3> : (const void *)k_sauvola_fused<1>;
-    static std::mutex mu;
-    static int occ_cache[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    int occ;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        int &oc = occ_cache[C == 3][nt == 128 ? 0 : (nt == 192 ? 1 : 2)];
-        if (!oc) {
-            B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem(256, C).total));
-            B200MRC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, kern, nt, L.total));
-            if (oc < 1) oc = 1;
-        }
-        occ = oc;
-    }
+    const FusedSmem L(nt, C, p.eb);
+    // occupancy variant: CTAs of 128 threads run 4 per SM with 128 registers (default) or 5 / 3 per SM (tuning key FUSED_OCC)
+    const int occ_req = nt == 128 ? tune(T_FUSED_OCC) : 0;
+    const void *kern;
+    if (nt == 128 && occ_req == 5) kern = C == 3 ? (const void *)k_sauvola_fused<3, 128, 5> : (const void *)k_sauvola_fused<1, 128, 5>;
+    else if (nt == 128 && occ_req == 3) kern = C == 3 ? (const void *)k_sauvola_fused<3, 128, 3> : (const void *)k_sauvola_fused<1, 128, 3>;
+    else kern = C == 3 ? (const void *)k_sauvola_fused<3, 256, 2> : (const void *)k_sauvola_fused<1, 256, 2>;
+    int occ = 0;
+    B200MRC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    B200MRC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, L.total));
+    if (occ < 1) occ = 1;
     // bands: warm-up costs about half a row per window row; pick the band count with the least modelled time
     const long slots = (long)dev_info().sm_count * occ;
     const long items0 = (long)N * p.n_strips;
@@ -559,8 +618,11 @@ namespace b200mrc {
 int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C,
                      uint8_t *out, int64_t out_pitch, int64_t out_stride,
                      int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st);
-// tuning key THRESHOLD_PATH = legacy keeps the two-pass form (A/B runs)
-bool threshold_path_legacy() { return tune(T_THRESHOLD_PATH) == 1; }
+// Tuning key THRESHOLD_PATH: fused (one kernel, sauvola_fused.cu) or legacy (gray_blur.cu + sauvola.cu).  Measured on B200
+// (profiles/r2_fused_threshold.md): the fused kernel moves half the bytes and executes 18 % fewer instructions, but its 96-128
+// registers per thread hold it at 16-20 warps per SM and 0.47 IPC, against 32-48 warps and 0.7 IPC for the two lean
+// kernels -- 4.7 ms against 3.5 ms for 64 RGB pages.  auto therefore picks the two-pass form.
+bool threshold_path_legacy() { return tune(T_THRESHOLD_PATH) != 2; }
 }  // namespace b200mrc
 
 extern "C" size_t b200mrc_threshold_workspace_bytes(int width, int height, int n_pages)

@@ -278,11 +278,13 @@ def _threshold_expected(orc, page, sig_est, ww, wh, k=0.34):
 
 @pytest.mark.parametrize('shape,rgb', [((70, 64), True), ((90, 131), False), ((300, 1003), True), ((131, 2000), False),
                                        ((420, 2550), True), ((64, 3000), True), ((1, 1), True), ((9, 40), False)])
-def test_threshold_mask_matches_oracle(eng, orc, shape, rgb):
+@pytest.mark.parametrize('path', ['fused', 'legacy'])
+def test_threshold_mask_matches_oracle(eng, orc, tuning, shape, rgb, path):
     """create_threshold_mask as one fused kernel (b200mrc_threshold_mask): gray conversion, per-page blur decision
     (radius 0, 1, 2 in-kernel; radius > 2 through the tiled pre-blur; NaN / <= 1.0: none), Sauvola.  Small pages take
     the two-pass fallback behind the same entry point."""
     import torch
+    tuning('THRESHOLD_PATH', path)
     h, w = shape
     rng = np.random.default_rng(h * 31 + w)
     sig_est = [0.5, 1.1, 1.3, 3.4, 4.0, 6.2, 9.0, 26.0, float('nan')]                    # radii 0 0 1 1 2 2 4 10 -
@@ -309,10 +311,11 @@ def test_threshold_mask_matches_oracle(eng, orc, shape, rgb):
         assert np.array_equal(got[i], _threshold_expected(orc, pages[i], None, 75, 75, k=0.2)), (shape, rgb, i)
 
 
-def test_fused_gray_all_colours(eng, orc):
+def test_fused_gray_all_colours(eng, orc, tuning):
     """The fused kernel's RGB -> L (two dp4a on the coefficient bytes) on all 2^24 colours: its gray delay-line plane
     (the threshold workspace) must equal PIL's convert('L')."""
     import torch
+    tuning('THRESHOLD_PATH', 'fused')
     allc = np.stack(np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing='ij'), -1)
     allc = allc.reshape(1, 4096, 4096, 3).astype(np.uint8)
     src = _plane(eng, allc)
@@ -328,13 +331,15 @@ def test_fused_gray_all_colours(eng, orc):
 
 
 @pytest.mark.parametrize('knobs', [{'FUSED_NT': 128, 'FUSED_BANDS': 1}, {'FUSED_NT': 192, 'FUSED_BANDS': 3},
-                                   {'FUSED_NT': 256, 'FUSED_BANDS': 7}, {'FUSED_NT': 128, 'FUSED_BANDS': 40}],
-                         ids=['nt128-1band', 'nt192-3bands', 'nt256-7bands', 'nt128-40bands'])
+                                   {'FUSED_NT': 256, 'FUSED_BANDS': 7}, {'FUSED_NT': 128, 'FUSED_BANDS': 40},
+                                   {'FUSED_NT': 128, 'FUSED_OCC': 5}, {'FUSED_NT': 128, 'FUSED_OCC': 3, 'FUSED_BANDS': 2}],
+                         ids=['nt128-1band', 'nt192-3bands', 'nt256-7bands', 'nt128-40bands', 'occ5', 'occ3'])
 def test_threshold_mask_geometries(eng, orc, tuning, knobs):
     """Every CTA width and several band heights (incl. bands shorter than the window) of the fused kernel, flags, and
     byte-identical results across launches (the gray delay line is rewritten by overlapping CTAs with equal bytes)."""
     import torch
     from archive_pdf_tools_b200 import _lib
+    tuning('THRESHOLD_PATH', 'fused')
     for k_, v in knobs.items():
         tuning(k_, v)
     rng = np.random.default_rng(3)

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--pages', type=int, nargs='+', default=[64])
+    ap.add_argument('--pages', type=str, default='64', help='batch sizes, comma separated')
     ap.add_argument('--distinct', type=int, default=4)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--shape', type=int, nargs=2, default=[3300, 2550])
@@ -36,7 +36,7 @@ def main():
     window = pkg.window_for_dpi(a.dpi)
     distinct = [synth.make_page(i, H, W, dpi=a.dpi, rgb=not a.gray, halftone=a.halftone and i % 3 == 0) for i in range(a.distinct)]
     eng = pkg.get_engine()
-    for npages in a.pages:
+    for npages in [int(v) for v in a.pages.split(',')]:
         pages = np.stack([distinct[i % a.distinct] for i in range(npages)])
         ref = None
         for v in a.variants:
