@@ -24,6 +24,15 @@ class Rect(C.Structure):
     _fields_ = [('ptr', vp), ('pitch', i64), ('width', C.c_int32), ('height', C.c_int32), ('keys', vp)]
 
 
+class CopyRect(C.Structure):
+    _fields_ = [('src', vp), ('src_pitch', i64), ('dst', vp), ('dst_pitch', i64), ('width', C.c_int32), ('height', C.c_int32)]
+
+
+class SauvolaItem(C.Structure):
+    _fields_ = [('in_', vp), ('in_pitch', i64), ('out', vp), ('out_pitch', i64), ('width', C.c_int32), ('height', C.c_int32),
+                ('flags', C.c_int32), ('reserved', C.c_int32)]
+
+
 class DecomposeArgs(C.Structure):
     _fields_ = [
         ('img', vp), ('img_pitch', i64), ('img_page_stride', i64), ('channels', C.c_int),
@@ -69,6 +78,8 @@ PROTOTYPES = {
     'b200mrc_resample_plan_out_size': (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'b200mrc_resample_workspace_bytes': (C.c_size_t, [vp, C.c_int]),
     'b200mrc_resample': (C.c_int, [vp, vp, i64, i64, vp, i64, i64, C.c_int, vp, C.c_size_t, vp]),
+    'b200mrc_rects_copy': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
+    'b200mrc_sauvola_items': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp]),
     'b200mrc_rects_count_nonzero': (C.c_int, [vp, C.c_int, vp, vp]),
     'b200mrc_rects_sigma_bool': (C.c_int, [vp, C.c_int, vp, vp]),
     'b200mrc_pack_mask': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

@@ -39,6 +39,17 @@ __global__ void __launch_bounds__(256) k_rects_count_nonzero(const b200mrc_rect 
     if (threadIdx.x == 0) counts[blockIdx.x] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
 }
 
+// n independent 2-D byte copies (line-crop gather / mask pastes): grid.z = rectangle, a CTA copies 8 rows x 1024 bytes
+__global__ void __launch_bounds__(256) k_rects_copy(const b200mrc_copy_rect *rects)
+{
+    const b200mrc_copy_rect r = rects[blockIdx.z];
+    const int y0 = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y0 >= r.height) return;
+    const uint8_t *s = r.src + (int64_t)y0 * r.src_pitch;
+    uint8_t *d = r.dst + (int64_t)y0 * r.dst_pitch;
+    for (int x = blockIdx.x * 1024 + (threadIdx.x & 31); x < min(r.width, (int)(blockIdx.x + 1) * 1024); x += 32) d[x] = s[x];
+}
+
 // f2  mask hand-off to the encoder (encode_mrc_mask, mrc.py:474-520: Image.fromarray(np_mask).save(png)): the
 // boolean mask as PIL mode-'1' rows, 8 pixels per byte, most significant bit first (== np.packbits(mask, axis=1)),
 // optionally inverted (recode.py:408: np_mask ^ True for --bw-pdf).  One thread per output byte.
@@ -155,6 +166,17 @@ extern "C" int b200mrc_rects_count_nonzero(const b200mrc_rect *rects_dev, int n_
     if (n_rects < 0 || (n_rects && (!rects_dev || !counts_dev))) return B200MRC_ERR_INVALID;
     if (n_rects == 0) return B200MRC_OK;
     { ProfScope _ps("k_rects_count_nonzero", (cudaStream_t)stream); k_rects_count_nonzero<<<n_rects, 256, 0, (cudaStream_t)stream>>>(rects_dev, counts_dev); }
+    B200MRC_LAUNCH_CHECK();
+    return B200MRC_OK;
+}
+
+extern "C" int b200mrc_rects_copy(const b200mrc_copy_rect *rects_dev, int n_rects, int max_width, int max_height, void *stream)
+{
+    if (n_rects < 0 || (n_rects && (!rects_dev || max_width <= 0 || max_height <= 0))) return B200MRC_ERR_INVALID;
+    if (n_rects == 0) return B200MRC_OK;
+    if (n_rects > 65535 || cdiv(max_height, 8) > 65535) return B200MRC_ERR_UNSUPPORTED;
+    dim3 grid(cdiv(max_width, 1024), cdiv(max_height, 8), n_rects);
+    { ProfScope _ps("k_rects_copy", (cudaStream_t)stream); k_rects_copy<<<grid, 256, 0, (cudaStream_t)stream>>>(rects_dev); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

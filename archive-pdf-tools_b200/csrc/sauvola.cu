@@ -74,15 +74,11 @@ __device__ __forceinline__ void scan_up2(uint32_t &a, uint32_t &b, int d)
         : "+r"(a), "+r"(b) : "r"(d));
 }
 
-template <bool KNEG, bool WIDE, int MINB>
-__global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams p)
+template <bool KNEG, bool WIDE>
+__device__ __forceinline__ void sauvola_mask_body(const SauvolaParams &p, const int bx, const int page, uint2 *sP, uint2 *sWT)
 {
-    __shared__ uint2 sP[2 * SPN];
-    __shared__ uint2 sWT[2 * WTN];
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
-    const int page = blockIdx.y;
+    const int strip = bx % p.n_strips, band = bx / p.n_strips;
     const int sx0 = strip * p.strip_w;
     const int ex0 = sx0 - p.ext_left;             // first input column of this CTA (multiple of 4)
     const int by0 = band * p.band_h;
@@ -258,6 +254,43 @@ __global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams
     if (y < by1) step(IntC<0>(), y);
 }
 
+template <bool KNEG, bool WIDE, int MINB>
+__global__ void __launch_bounds__(ST, MINB) k_sauvola_mask_w(const SauvolaParams p)
+{
+    __shared__ uint2 sP[2 * SPN];
+    __shared__ uint2 sWT[2 * WTN];
+    sauvola_mask_body<KNEG, WIDE>(p, (int)blockIdx.x, (int)blockIdx.y, sP, sWT);
+}
+
+// strip / band geometry of an image of the given width (shared by the launcher and the items kernel)
+__host__ __device__ __forceinline__ void sauvola_geometry(SauvolaParams &p, int width, int height)
+{
+    p.W = width; p.H = height;
+    p.ext_left = (p.l - 1 + 3) / 4 * 4;
+    const int sw_max = (SE - p.ext_left - p.r) / 4 * 4;          // >= 768
+    p.n_strips = (width + sw_max - 1) / sw_max;
+    p.strip_w = ((width + p.n_strips - 1) / p.n_strips + 3) / 4 * 4;
+    p.band_h = 128;
+    p.n_bands = (height + p.band_h - 1) / p.band_h;
+}
+
+// One launch over a device array of independent images (the text-line crops of create_hocr_mask, mrc.py:226-236):
+// blockIdx.y = item, blockIdx.x = (strip, band) of that item; CTAs beyond an item's own grid leave at once.
+template <bool KNEG, bool WIDE>
+__global__ void __launch_bounds__(ST, 4) k_sauvola_items(const b200mrc_sauvola_item *items, const SauvolaParams base)
+{
+    __shared__ uint2 sP[2 * SPN];
+    __shared__ uint2 sWT[2 * WTN];
+    const b200mrc_sauvola_item it = items[blockIdx.y];
+    SauvolaParams p = base;
+    p.in = it.in; p.in_pitch = it.in_pitch; p.in_stride = 0;
+    p.out = it.out; p.out_pitch = it.out_pitch; p.out_stride = 0;
+    p.flags = it.flags;
+    sauvola_geometry(p, it.width, it.height);
+    if ((int)blockIdx.x >= p.n_strips * p.n_bands) return;
+    sauvola_mask_body<KNEG, WIDE>(p, (int)blockIdx.x, 0, sP, sWT);
+}
+
 }  // namespace
 
 bool sauvola_fused_ok(const uint8_t *src, int64_t src_pitch, int64_t src_stride, int C, const uint8_t *out, int64_t out_pitch,
@@ -296,15 +329,9 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
     SauvolaParams p;
     p.in = in; p.in_pitch = in_pitch; p.in_stride = in_page_stride;
     p.out = out; p.out_pitch = out_pitch; p.out_stride = out_page_stride;
-    p.W = width; p.H = height;
     p.l = (window_width + 1) / 2;  p.r = window_width / 2;
     p.o = (window_height + 1) / 2; p.u = window_height / 2;
-    p.ext_left = (p.l - 1 + 3) / 4 * 4;
-    const int sw_max = (SE - p.ext_left - p.r) / 4 * 4;          // >= 768
-    p.n_strips = cdiv(width, sw_max);
-    p.strip_w = (cdiv(width, p.n_strips) + 3) / 4 * 4;
-    p.band_h = 128;
-    p.n_bands = cdiv(height, p.band_h);
+    sauvola_geometry(p, width, height);
     p.km1 = k - 1.0;
     p.k2 = k * k / R / R;                                         // sauvola.pyx:60
     p.kneg = k < 0;
@@ -319,6 +346,34 @@ extern "C" int b200mrc_sauvola(const uint8_t *in, int64_t in_pitch, int64_t in_p
       } else if (wide) {
           k_sauvola_mask_w<false, true, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p);
       } else k_sauvola_mask_w<false, false, 4><<<grid, ST, 0, (cudaStream_t)stream>>>(p); }
+    B200MRC_LAUNCH_CHECK();
+    return B200MRC_OK;
+}
+
+extern "C" int b200mrc_sauvola_items(const b200mrc_sauvola_item *items_dev, int n_items, int max_width, int max_height,
+                                     int window_width, int window_height, double k, double R, void *stream)
+{
+    if (n_items < 0 || (n_items && (!items_dev || max_width <= 0 || max_height <= 0)) || !(R > 0)) return B200MRC_ERR_INVALID;
+    if (window_width < 1 || window_height < 1 || window_width > B200MRC_MAX_WINDOW || window_height > B200MRC_MAX_WINDOW)
+        return B200MRC_ERR_UNSUPPORTED;
+    if (n_items == 0) return B200MRC_OK;
+    if (n_items > 65535) return B200MRC_ERR_UNSUPPORTED;
+    SauvolaParams p;
+    memset(&p, 0, sizeof(p));
+    p.l = (window_width + 1) / 2;  p.r = window_width / 2;
+    p.o = (window_height + 1) / 2; p.u = window_height / 2;
+    sauvola_geometry(p, max_width, max_height);                    // the largest item sizes the grid
+    p.km1 = k - 1.0;
+    p.k2 = k * k / R / R;
+    p.kneg = k < 0;
+    dim3 grid((unsigned)(p.n_strips * p.n_bands), (unsigned)n_items);
+    const bool wide = window_width > 128;
+    { ProfScope _ps("k_sauvola_items", (cudaStream_t)stream);
+      if (p.kneg) {
+          if (wide) k_sauvola_items<true, true><<<grid, ST, 0, (cudaStream_t)stream>>>(items_dev, p);
+          else k_sauvola_items<true, false><<<grid, ST, 0, (cudaStream_t)stream>>>(items_dev, p);
+      } else if (wide) k_sauvola_items<false, true><<<grid, ST, 0, (cudaStream_t)stream>>>(items_dev, p);
+      else k_sauvola_items<false, false><<<grid, ST, 0, (cudaStream_t)stream>>>(items_dev, p); }
     B200MRC_LAUNCH_CHECK();
     return B200MRC_OK;
 }

@@ -110,13 +110,29 @@ def _iter_text_lines(hocr_word_data, image_width, image_height, downsample):
                 yield tuple(box)
 
 
+def _boxes_overlap(boxes):
+    """True if any two (left, top, right, bottom) boxes intersect (sweep over the sorted left edges)."""
+    order = sorted(range(len(boxes)), key=lambda i: boxes[i][0])
+    active = []
+    for i in order:
+        l, t, r, b = boxes[i]
+        active = [j for j in active if boxes[j][2] > l]
+        for j in active:
+            if boxes[j][1] < b and t < boxes[j][3]:
+                return True
+        active.append(i)
+    return False
+
+
 def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, timing_data=None):
     """mrc.py:188-270 on the device.  img: gray Plane (the plain 'L' page, n = 1); mask_arr: mask Plane, modified in
     place.  Per text line: Sauvola (k = 0.1) on the crop and on the inverted crop, polarity picked by fill ratio and,
     for the undecided lines, by mean_estimate_sigma of the two boolean results; the winner is pasted into the mask.
-    All lines of the page go through the device together: 3 small launches per line, then one count kernel, one
-    sigma kernel and the pastes (in line order, so overlapping boxes resolve like the reference's loop); the host
-    only takes the per-line decisions (two small D2H reads per page)."""
+    All line crops of the page go through the device TOGETHER: one gather launch (crops -> aligned scratch), one
+    Sauvola launch over both polarities of every crop (b200mrc_sauvola_items), one count launch, one sigma launch for
+    the undecided lines and one paste launch -- five launches and two small device-to-host reads per page, whatever
+    the number of lines.  The host only takes the per-line decisions (the reference's rule, _hocr_choice).  Pastes of
+    overlapping boxes keep the reference's loop order (they are then issued one by one)."""
     import ctypes as C
     t = time()
     lines = list(_iter_text_lines(hocr_word_data, img.w, img.h, downsample))
@@ -125,7 +141,7 @@ def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, t
         lib = L.lib()
         st = E._stream_ptr()
         window = E.window_for_dpi(dpi)
-        k = 0.1          # XXX (reference): If you tweak k, you must tweak the various ratio and sigma's
+        k = 0.1          # the reference's choice; its ratio / sigma limits below are tuned to it (mrc.py:228)
         # one scratch buffer: per line an aligned copy of the crop and the two threshold results
         geo, off = [], 0
         for (left, top, right, bottom) in lines:
@@ -136,26 +152,38 @@ def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, t
             off += 3 * size
         scratch = torch.empty(off, dtype=torch.uint8, device=eng.device)
         base = scratch.data_ptr()
-        for (left, top, right, bottom), (w, h, pitch, o_in, o_th, o_ti) in zip(lines, geo):
-            L.check(lib.b200mrc_copy2d(C.c_void_p(base + o_in), pitch, C.c_void_p(img.t.data_ptr() + top * img.pitch + left), img.pitch,
-                                       w, h, L.COPY_D2D, st), 'b200mrc_copy2d')
-            for o_out, flags in ((o_th, 0), (o_ti, L.SAUVOLA_INVERT_INPUT)):
-                L.check(lib.b200mrc_sauvola(C.c_void_p(base + o_in), pitch, pitch * h, C.c_void_p(base + o_out), pitch, pitch * h,
-                                            w, h, 1, window, window, k, 128.0, flags, st), 'b200mrc_sauvola')
+        max_w, max_h = max(g[0] for g in geo), max(g[1] for g in geo)
 
-        def rects(items):                                    # items: (ptr, pitch, w, h, keys_ptr)
-            arr = (L.Rect * len(items))()
-            for r, (ptr, pitch, w, h, keys) in zip(arr, items):
+        def upload(structs):
+            """ctypes array of descriptor structs -> device tensor (one small H2D copy)."""
+            return torch.frombuffer(bytearray(bytes(structs)), dtype=torch.uint8).to(eng.device)
+
+        # ---- gather the crops (aligned rows for the Sauvola kernel) and threshold both polarities, one launch each
+        crops = (L.CopyRect * len(lines))()
+        items = (L.SauvolaItem * (2 * len(lines)))()
+        for i, ((left, top, right, bottom), (w, h, pitch, o_in, o_th, o_ti)) in enumerate(zip(lines, geo)):
+            c = crops[i]
+            c.src, c.src_pitch, c.dst, c.dst_pitch, c.width, c.height = img.t.data_ptr() + top * img.pitch + left, img.pitch, base + o_in, pitch, w, h
+            for j, (o_out, flags) in enumerate(((o_th, 0), (o_ti, L.SAUVOLA_INVERT_INPUT))):
+                it = items[2 * i + j]
+                it.in_, it.in_pitch, it.out, it.out_pitch, it.width, it.height, it.flags = base + o_in, pitch, base + o_out, pitch, w, h, flags
+        crops_d, items_d = upload(crops), upload(items)
+        L.check(lib.b200mrc_rects_copy(C.c_void_p(crops_d.data_ptr()), len(lines), max_w, max_h, st), 'b200mrc_rects_copy')
+        L.check(lib.b200mrc_sauvola_items(C.c_void_p(items_d.data_ptr()), 2 * len(lines), max_w, max_h, window, window, k, 128.0, st),
+                'b200mrc_sauvola_items')
+
+        def rects(entries):                                  # entries: (ptr, pitch, w, h, keys_ptr)
+            arr = (L.Rect * len(entries))()
+            for r, (ptr, pitch, w, h, keys) in zip(arr, entries):
                 r.ptr, r.pitch, r.width, r.height, r.keys = ptr, pitch, w, h, keys
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            return host.to(eng.device)
+            return upload(arr)
 
-        items = []
+        entries = []
         for (w, h, pitch, o_in, o_th, o_ti) in geo:
-            items += [(base + o_th, pitch, w, h, 0), (base + o_ti, pitch, w, h, 0)]
-        rd = rects(items)
-        counts = torch.empty(len(items), dtype=torch.int32, device=eng.device)
-        L.check(lib.b200mrc_rects_count_nonzero(C.c_void_p(rd.data_ptr()), len(items), C.c_void_p(counts.data_ptr()), st),
+            entries += [(base + o_th, pitch, w, h, 0), (base + o_ti, pitch, w, h, 0)]
+        rd = rects(entries)
+        counts = torch.empty(len(entries), dtype=torch.int32, device=eng.device)
+        L.check(lib.b200mrc_rects_count_nonzero(C.c_void_p(rd.data_ptr()), len(entries), C.c_void_p(counts.data_ptr()), st),
                 'b200mrc_rects_count_nonzero')
         counts = counts.cpu().tolist()
         ratios = []
@@ -166,27 +194,38 @@ def create_hocr_mask(img, mask_arr, hocr_word_data, downsample=None, dpi=None, t
         need = [i for i, (r, ri) in enumerate(ratios) if _needs_sigma(r, ri)]
         sig = {}
         if need:
-            koff, kitems = 0, []
+            koff, kentries = 0, []
             for i in need:
                 w, h, pitch, o_in, o_th, o_ti = geo[i]
                 nk = ((h + 3) // 2) * ((w + 3) // 2) * 8
-                kitems += [(base + o_th, pitch, w, h, koff), (base + o_ti, pitch, w, h, koff + nk)]
+                kentries += [(base + o_th, pitch, w, h, koff), (base + o_ti, pitch, w, h, koff + nk)]
                 koff += 2 * nk
             keys = torch.empty(max(koff, 8), dtype=torch.uint8, device=eng.device)
-            kitems = [(p_, pi, w, h, keys.data_ptr() + ko) for (p_, pi, w, h, ko) in kitems]
-            kd = rects(kitems)
-            sg = torch.empty(len(kitems), dtype=torch.float64, device=eng.device)
-            L.check(lib.b200mrc_rects_sigma_bool(C.c_void_p(kd.data_ptr()), len(kitems), C.c_void_p(sg.data_ptr()), st),
+            kentries = [(p_, pi, w, h, keys.data_ptr() + ko) for (p_, pi, w, h, ko) in kentries]
+            kd = rects(kentries)
+            sg = torch.empty(len(kentries), dtype=torch.float64, device=eng.device)
+            L.check(lib.b200mrc_rects_sigma_bool(C.c_void_p(kd.data_ptr()), len(kentries), C.c_void_p(sg.data_ptr()), st),
                     'b200mrc_rects_sigma_bool')
             sg = sg.cpu().tolist()
             for j, i in enumerate(need):
                 sig[i] = (sg[2 * j], sg[2 * j + 1])
+        # ---- pastes: mask_arr[top:bottom, left:right] = th for the lines that got a polarity
+        chosen = []
         for i, ((left, top, right, bottom), (w, h, pitch, o_in, o_th, o_ti)) in enumerate(zip(lines, geo)):
             c = _hocr_choice(ratios[i][0], ratios[i][1], sig.get(i))
             if c:
-                L.check(lib.b200mrc_copy2d(C.c_void_p(mask_arr.t.data_ptr() + top * mask_arr.pitch + left), mask_arr.pitch,
-                                           C.c_void_p(base + (o_th if c == 1 else o_ti)), pitch, w, h, L.COPY_D2D, st), 'b200mrc_copy2d')
-        torch.cuda.current_stream().synchronize()           # scratch buffers stay alive until the pastes are done
+                chosen.append((mask_arr.t.data_ptr() + top * mask_arr.pitch + left, base + (o_th if c == 1 else o_ti), pitch, w, h, lines[i]))
+        if chosen and not _boxes_overlap([c[5] for c in chosen]):
+            pastes = (L.CopyRect * len(chosen))()
+            for p_, (dst, src, pitch, w, h, _box) in zip(pastes, chosen):
+                p_.src, p_.src_pitch, p_.dst, p_.dst_pitch, p_.width, p_.height = src, pitch, dst, mask_arr.pitch, w, h
+            pastes_d = upload(pastes)
+            L.check(lib.b200mrc_rects_copy(C.c_void_p(pastes_d.data_ptr()), len(chosen), max(c[3] for c in chosen), max(c[4] for c in chosen), st),
+                    'b200mrc_rects_copy')
+        else:
+            for (dst, src, pitch, w, h, _box) in chosen:     # overlapping boxes: the later line wins, as in the reference's loop
+                L.check(lib.b200mrc_copy2d(C.c_void_p(dst), mask_arr.pitch, C.c_void_p(src), pitch, w, h, L.COPY_D2D, st), 'b200mrc_copy2d')
+        torch.cuda.current_stream().synchronize()           # scratch and descriptor buffers stay alive until the pastes are done
     if timing_data is not None:
         timing_data.append(('hocr_mask_gen', time() - t))
     return len(lines)

@@ -441,7 +441,32 @@ def main():
         torch.cuda.synchronize()
         barrier()
         dt = max_ranks(time.time() - t0)
+        # the platform ceiling of exactly this transfer pattern: every step's H2D and D2H bytes, both directions at once,
+        # all ranks concurrently, no kernels (what the host<->device path of this box can deliver at N GPUs)
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        dev_in = torch.empty_like(host, device='cuda')
+        dev_out = {k: torch.empty_like(v, device='cuda') for k, v in outs2[0].items()}
+
+        def copy_only():
+            with torch.cuda.stream(s_h2d):
+                dev_in.copy_(host, non_blocking=True)
+            with torch.cuda.stream(s_d2h):
+                for k, v in outs2[0].items():
+                    v.copy_(dev_out[k], non_blocking=True)
+
+        copy_only(); torch.cuda.synchronize(); barrier()
+        t0 = time.time()
+        for _ in range(3):
+            copy_only()
+        torch.cuda.synchronize()
+        barrier()
+        dt_copy = max_ranks((time.time() - t0) / 3)
+        del dev_in, dev_out
         e2e = {'value': px_step * e2e_steps / dt / 1e6, 'unit': 'Mpixels/s', 'steps': e2e_steps,
+               'copy_only_ms_per_step': dt_copy * 1e3, 'ms_per_step': dt / e2e_steps * 1e3,
+               'frac_of_copy_ceiling': dt_copy / (dt / e2e_steps),
+               'copy_ceiling_note': 'copy_only = the same H2D + D2H bytes per step on two streams, no kernels, all ranks at once: the '
+                                    'host<->device ceiling of this box at this N; frac = copy_only time / e2e step time',
                'h2d_bytes_per_step': int(host.numel()) * world,
                'd2h_bytes_per_step': int(sum(v.numel() for v in outs2[0].values())) * world,
                'one_call_at_a_time': px_step * e2e_steps / dt_sync / 1e6, 'batches_in_flight': 2, 'packed_mask': e2e_packed,

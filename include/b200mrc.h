@@ -180,6 +180,22 @@ B200MRC_API int    b200mrc_resample(const b200mrc_resample_plan *plan,
 typedef struct {
     const uint8_t *ptr; int64_t pitch; int32_t width, height; uint64_t *keys;
 } b200mrc_rect;
+/* The line crops of a page as ONE launch each (mrc.py:188-270 walks them one by one):
+ *   b200mrc_rects_copy    : n 2-D byte copies described by a DEVICE array (crop gather into aligned scratch, and the
+ *                           pastes `mask_arr[top:bottom, left:right] = th`, mrc.py:266); the rectangles of one call must
+ *                           not overlap in their destinations.
+ *   b200mrc_sauvola_items : b200mrc_sauvola on n independent single-channel images (each item is thresholded as an
+ *                           image of its own: windows clamp at the item's borders); per-item flags B200MRC_SAUVOLA_*.
+ * max_width / max_height: the largest item (sizes the launch grid). */
+typedef struct {
+    const uint8_t *src; int64_t src_pitch; uint8_t *dst; int64_t dst_pitch; int32_t width, height;
+} b200mrc_copy_rect;
+typedef struct {
+    const uint8_t *in; int64_t in_pitch; uint8_t *out; int64_t out_pitch; int32_t width, height, flags, reserved;
+} b200mrc_sauvola_item;
+B200MRC_API int b200mrc_rects_copy(const b200mrc_copy_rect *rects_dev, int n_rects, int max_width, int max_height, void *stream);
+B200MRC_API int b200mrc_sauvola_items(const b200mrc_sauvola_item *items_dev, int n_items, int max_width, int max_height,
+                          int window_width, int window_height, double k, double R, void *stream);
 B200MRC_API int b200mrc_rects_count_nonzero(const b200mrc_rect *rects_dev, int n_rects, uint32_t *counts_dev, void *stream);
 B200MRC_API int b200mrc_rects_sigma_bool(const b200mrc_rect *rects_dev, int n_rects, double *sigma_dev, void *stream);
 

@@ -1,24 +1,64 @@
 #!/usr/bin/env python
-"""Host<->device copy ceilings of this box: pinned 1-D copies each way, both ways at once, and pitched 2-D copies."""
-import time, torch, ctypes as C, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-n = 1 << 30
-h = torch.empty(n, dtype=torch.uint8).pin_memory(); h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
-d = torch.empty(n, dtype=torch.uint8, device='cuda'); d2 = torch.empty(n, dtype=torch.uint8, device='cuda')
-s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-def t(fn, reps=5):
-    fn(); torch.cuda.synchronize(); t0 = time.time()
-    for _ in range(reps): fn()
-    torch.cuda.synchronize(); return (time.time() - t0) / reps
-a = t(lambda: d.copy_(h, non_blocking=True)); print('H2D 1D  %.1f GB/s' % (n / a / 1e9))
-b = t(lambda: h2.copy_(d2, non_blocking=True)); print('D2H 1D  %.1f GB/s' % (n / b / 1e9))
-def both():
-    with torch.cuda.stream(s1): d.copy_(h, non_blocking=True)
-    with torch.cuda.stream(s2): h2.copy_(d2, non_blocking=True)
-c = t(both); print('both    %.1f GB/s each (%.1f total)' % (n / c / 1e9, 2 * n / c / 1e9))
-from archive_pdf_tools_b200 import _lib
-L = _lib.lib()
-row, pitch = 7650, 7664; rows = n // pitch
-st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-e = t(lambda: L.b200mrc_copy2d(C.c_void_p(d.data_ptr()), pitch, C.c_void_p(h.data_ptr()), row, row, rows, 1, st)); print('H2D 2D  %.1f GB/s' % (row * rows / e / 1e9))
-f = t(lambda: L.b200mrc_copy2d(C.c_void_p(h2.data_ptr()), row, C.c_void_p(d2.data_ptr()), pitch, row, rows, 2, st)); print('D2H 2D  %.1f GB/s' % (row * rows / f / 1e9))
+"""Host<->device copy ceilings of this box, one process per GPU (plain python for one GPU, torchrun for N): pinned 1-D
+copies each way and both ways at once, all ranks copying concurrently after a barrier.  Rank 0 prints one JSON line with
+the per-GPU and the aggregate rates (max time over ranks) -- the ceiling the end-to-end path (bench.py `e2e`) runs against.
+
+  python tools/pcie_bw.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 tools/pcie_bw.py
+"""
+import json, os, sys, time
+import torch
+import torch.distributed as dist
+
+
+def main():
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('LOCAL_RANK', 0), ('WORLD_SIZE', 1)))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    n = 1 << 30
+    h = torch.empty(n, dtype=torch.uint8).pin_memory(); h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device='cuda'); d2 = torch.empty(n, dtype=torch.uint8, device='cuda')
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps=5):
+        fn(); sync(); t0 = time.time()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.time() - t0) / reps], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        sync()
+        return float(dt.item())
+
+    def both():
+        with torch.cuda.stream(s1):
+            d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+
+    a = timed(lambda: d.copy_(h, non_blocking=True))
+    b = timed(lambda: h2.copy_(d2, non_blocking=True))
+    c = timed(both)
+    if rank == 0:
+        gb = n / 1e9
+        print(json.dumps({'n_gpus': world, 'bytes_per_copy': n,
+                          'h2d_GB_s_per_gpu': gb / a, 'd2h_GB_s_per_gpu': gb / b, 'duplex_GB_s_per_gpu_each_way': gb / c,
+                          'h2d_GB_s_aggregate': world * gb / a, 'd2h_GB_s_aggregate': world * gb / b,
+                          'duplex_GB_s_aggregate_total': 2 * world * gb / c,
+                          'cpus': len(os.sched_getaffinity(0)),
+                          'note': 'all ranks copy concurrently; times are the max over ranks'}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
