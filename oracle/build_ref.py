@@ -31,8 +31,37 @@ def have_ref():
     return all(os.path.exists(ref_so_path(n)) for n in ('sauvola', 'optimiser'))
 
 
+# The reference's Python glue as byte code: internetarchivepdf/{mrc,const,jpeg2000}.py compiled (py_compile, unmodified)
+# into oracle/_ref/internetarchivepdf/*.pyc, so that the GPU box -- where /root/reference does not exist -- can run the
+# UNMODIFIED reference create_mrc_hocr_components on top of the drop-in `sauvola` / `optimiser` modules
+# (tests/test_gpu_pipeline.py::test_unmodified_reference_through_install).  Built artefacts only; no source is copied.
+GLUE = ('mrc', 'const', 'jpeg2000')
+GLUE_DIR = os.path.join(OUT, 'internetarchivepdf')
+
+
+def have_glue():
+    return all(os.path.exists(os.path.join(GLUE_DIR, n + '.pyc')) for n in GLUE)
+
+
+def build_glue(force=False):
+    if have_glue() and not force:
+        return True
+    srcs = [os.path.join(REF, 'internetarchivepdf', n + '.py') for n in GLUE]
+    if not all(os.path.exists(p) for p in srcs):
+        return have_glue()
+    import py_compile
+    os.makedirs(GLUE_DIR, exist_ok=True)
+    for n, p in zip(GLUE, srcs):
+        py_compile.compile(p, cfile=os.path.join(GLUE_DIR, n + '.pyc'), doraise=True)
+    return have_glue()
+
+
 def build(force=False, verbose=False):
     """Returns True if oracle/_ref is usable after the call."""
+    try:
+        build_glue(force)
+    except Exception:
+        pass
     if have_ref() and not force:
         return True
     pyx = [os.path.join(REF, 'cython', n + '.pyx') for n in ('sauvola', 'optimiser')]

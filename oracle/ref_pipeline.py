@@ -117,10 +117,28 @@ def load_reference_mrc(reference_dir='/root/reference'):
     """Import the UNMODIFIED reference internetarchivepdf/mrc.py (container only).  Third-party
     modules that are not installed are stubbed: fitz (only fitz.TOOLS.set_icc is touched at
     import, mrc.py:39-41) and skimage, whose estimate_sigma is bound to the oracle restatement."""
-    mrc_path = os.path.join(reference_dir, 'internetarchivepdf', 'mrc.py')
+    return _load_reference_mrc(reference_dir, dropin=False)
+
+
+def load_reference_mrc_on_dropin(reference_dir='/root/reference'):
+    """The UNMODIFIED reference mrc.py on top of whatever top-level `sauvola` / `optimiser` modules are importable --
+    i.e. the GPU drop-ins after archive_pdf_tools_b200.install().  Falls back to the byte-compiled glue in
+    oracle/_ref/internetarchivepdf (build_ref.build_glue) where the reference checkout does not exist (GPU box)."""
+    return _load_reference_mrc(reference_dir, dropin=True)
+
+
+def _load_reference_mrc(reference_dir, dropin):
+    pkg_dir = os.path.join(reference_dir, 'internetarchivepdf')
+    mrc_path = os.path.join(pkg_dir, 'mrc.py')
     if not os.path.exists(mrc_path):
-        return None
-    sauvola, optimiser = ref_modules()
+        if not dropin or not build_ref.have_glue():
+            return None
+        pkg_dir = build_ref.GLUE_DIR
+        mrc_path = os.path.join(pkg_dir, 'mrc.pyc')
+    if dropin:
+        import sauvola, optimiser                            # the drop-in modules (install() put them on sys.path)
+    else:
+        sauvola, optimiser = ref_modules()
     saved = {k: sys.modules.get(k) for k in ('sauvola', 'optimiser', 'fitz', 'skimage', 'skimage.filters',
                                              'skimage.restoration', 'internetarchivepdf',
                                              'internetarchivepdf.jpeg2000', 'internetarchivepdf.const')}
@@ -145,10 +163,14 @@ def load_reference_mrc(reference_dir='/root/reference'):
     skr.estimate_sigma = estimate_sigma
     sys.modules.update({'skimage': sk, 'skimage.filters': skf, 'skimage.restoration': skr})
     pkg = types.ModuleType('internetarchivepdf')
-    pkg.__path__ = [os.path.join(reference_dir, 'internetarchivepdf')]
+    pkg.__path__ = [pkg_dir]
     sys.modules['internetarchivepdf'] = pkg
     try:
-        spec = importlib.util.spec_from_file_location('internetarchivepdf.mrc', mrc_path)
+        if mrc_path.endswith('.pyc'):
+            loader = importlib.machinery.SourcelessFileLoader('internetarchivepdf.mrc', mrc_path)
+            spec = importlib.util.spec_from_loader('internetarchivepdf.mrc', loader, origin=mrc_path)
+        else:
+            spec = importlib.util.spec_from_file_location('internetarchivepdf.mrc', mrc_path)
         mod = importlib.util.module_from_spec(spec)
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')

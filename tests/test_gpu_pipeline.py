@@ -367,3 +367,72 @@ def test_batched_decompose_with_hocr_matches_oracle(eng, synth, orc):
         assert np.array_equal(res['fg'][i], exp['fg']) and np.array_equal(res['bg'][i], exp['bg']), i
     plain = pkg.decompose_pages(pages, dpi=dpi, bg_downsample=3, denoise_mask='fast')
     assert not np.array_equal(plain['mask'][0], res['mask'][0]) and np.array_equal(plain['mask'][1], res['mask'][1])
+
+
+@pytest.mark.parametrize('name', golden_cases()[:3] + hocr_cases()[:2])
+def test_unmodified_reference_through_install(eng, synth, orc, name):
+    """Drop-in smoke through the reference's own call site: install() publishes the GPU `sauvola` / `optimiser`
+    modules, then the UNMODIFIED reference internetarchivepdf/mrc.py (byte-compiled into oracle/_ref by
+    oracle/build_ref.py, or the checkout itself in the build container) runs create_mrc_hocr_components on top of
+    them, like recode.py:400-406 / 427-433 and bin/compress-pdf-images:66-70 do.  Outputs must equal the golden
+    fixtures (made by the same reference code on its own Cython)."""
+    from PIL import Image
+    import archive_pdf_tools_b200 as pkg
+    from oracle import ref_pipeline
+    pkg.install(patch_reference=False)
+    ref = ref_pipeline.load_reference_mrc_on_dropin()
+    if ref is None:
+        pytest.skip('reference glue not available (oracle/_ref/internetarchivepdf not built)')
+    assert ref.binarise_sauvola.__module__ == 'sauvola' and ref.optimise_rgb2.__module__ == 'optimiser'
+    import sauvola
+    assert sauvola.__file__.startswith(pkg.DROPIN_DIR)
+    if name.startswith('hocr_'):
+        g = load_hocr_golden(name, synth)
+        kw = dict(dpi=g['dpi'], downsample=g['downsample'], bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'])
+        hocr = g['hocr']
+    else:
+        g = load_golden(name, synth)
+        kw = dict(dpi=g['dpi'], bg_downsample=g['bg_downsample'], fg_downsample=g['fg_downsample'], denoise_mask=g['denoise'])
+        hocr = []
+    timing, errors = [], set()
+    mask, fg, bg = list(ref.create_mrc_hocr_components(Image.fromarray(g['page']), hocr, timing_data=timing, errors=errors, **kw))
+    assert np.array_equal(mask, g['mask']), int((mask != g['mask']).sum())
+    assert np.array_equal(fg, g['fg']) and np.array_equal(bg, g['bg'])
+    assert [k for k, _ in timing] == g['timing_keys']
+
+
+def test_install_rebinds_an_imported_reference(eng, synth):
+    """install(patch_reference=True) with internetarchivepdf.mrc already imported: its pixel-path names are rebound."""
+    import sys
+    import archive_pdf_tools_b200 as pkg
+    from oracle import ref_pipeline
+    pkg.install(patch_reference=False)
+    ref = ref_pipeline.load_reference_mrc_on_dropin()
+    if ref is None:
+        pytest.skip('reference glue not available')
+    sys.modules['internetarchivepdf.mrc'] = ref
+    try:
+        pkg.install(patch_reference=True)
+        assert ref.create_mrc_hocr_components is pkg.create_mrc_hocr_components
+        assert ref.threshold_image is pkg.threshold_image
+        page = synth.make_page(4, 120, 90, dpi=100, rgb=False)
+        assert np.array_equal(ref.threshold_image(page, 100), pkg.threshold_image(page, 100))
+    finally:
+        sys.modules.pop('internetarchivepdf.mrc', None)
+
+
+def test_streamed_decomposer_packed_mask(eng, synth):
+    """packed_mask=True returns PIL mode-'1' rows (np.packbits) instead of the bool plane; fg / bg unchanged."""
+    import torch
+    import archive_pdf_tools_b200 as pkg
+    from archive_pdf_tools_b200.engine import StreamedDecomposer
+    pages = np.stack([synth.make_page(400 + i, 130, 203, dpi=100) for i in range(5)])
+    ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
+    host = torch.from_numpy(pages).pin_memory()
+    sd = StreamedDecomposer(eng, 5, 130, 203, 3, chunk=2, bg_downsample=3, packed_mask=True)
+    out = sd.alloc_outputs()
+    sd.run(host, out, 25, denoise_mask='fast')
+    assert out['mask'].shape == (5, 130, (203 + 7) // 8)
+    assert np.array_equal(out['mask'].numpy(), np.packbits(ref['mask'], axis=-1))
+    assert np.array_equal(out['fg'].numpy().reshape(ref['fg'].shape), ref['fg'])
+    assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])

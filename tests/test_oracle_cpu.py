@@ -232,7 +232,7 @@ def test_db2_filter_is_the_published_one():
 
 def test_special_gray_logic_equals_the_imported_reference(orc, synth):
     """grayconvert.py imported UNMODIFIED with only skimage.color.rgb2hsv stubbed (V = max, S = (max - min) / max on
-    the /255 floats, skimage's documented definition): statistics, bright_adjust, thresholds, level_arr and the
+    the uint8 * (1 / 255) floats, skimage's documented definition): statistics, bright_adjust, thresholds, level_arr and the
     lightness formula are then the reference's own code."""
     import importlib.util
     import sys
@@ -242,7 +242,7 @@ def test_special_gray_logic_equals_the_imported_reference(orc, synth):
         pytest.skip('reference checkout not present (container-only test)')
 
     def rgb2hsv(rgb):
-        arr = np.asarray(rgb).astype(np.float64) / 255.0
+        arr = np.multiply(np.asarray(rgb), 1.0 / 255, dtype=np.float64)     # skimage img_as_float: multiply by 1 / imax
         v = arr.max(-1)
         delta = v - arr.min(-1)
         with np.errstate(invalid='ignore', divide='ignore'):
