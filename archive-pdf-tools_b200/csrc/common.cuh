@@ -53,7 +53,7 @@ enum TuneKey {
     T_FUSED_BANDS,      // fused threshold: row bands per strip (0 auto)
     T_FUSED_DBG,        // fused threshold: timing experiments (skip parts of the kernel; results are wrong)
     T_FUSED_OCC,        // fused threshold, 128-thread CTAs: CTAs per SM the kernel is compiled for (0 = 4; 3 | 5)
-    T_THRESHOLD_PATH,   // 0 auto (the faster one: two-pass today), 1 two-pass (gray_blur + sauvola), 2 fused   env: legacy | fused
+    T_THRESHOLD_PATH,   // 0 auto (fused where it applies), 1 two-pass (gray_blur + sauvola kernels), 2 fused      env: legacy | fused
     T_OPT_PATH,         // 0 split (FIR + sweep), 1 generic fused sweep                                    env: generic
     T_NOISE_DIRECT,     // 1: one-thread-per-coefficient wavelet kernel
     T_RESAMPLE_2PASS,   // 1: separate horizontal / vertical resample kernels

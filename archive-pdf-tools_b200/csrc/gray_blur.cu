@@ -25,6 +25,7 @@ struct GrayBlurParams {
     const double *sigma;     // device, per page, may be null
     int *err;                // device error flag (radius out of range), may be null
     int rlo;                 // tiled kernel: smallest radius it handles (5 when the fast kernel ran, else 0)
+    int fast_rmin;           // fast kernel: smallest radius it handles (0; 3 behind the fused threshold kernel)
 };
 
 __device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch, int C, int y, int x)
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256, MINB) k_gray_blur_fast(const GrayBlurPara
     const int page = blockIdx.z;
     double sigma;
     const int radius = page_radius(p, page, sigma);
-    if (radius > 4) return;                    // the tiled kernels own this page
+    if (radius > 4 || radius < p.fast_rmin) return;   // the tiled kernels / the fused threshold kernel own this page
     if (radius > 0) blur_weights(radius, sigma, sw, sphi);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int by0 = (blockIdx.y * 8 + warp) * FB_BAND;
@@ -274,7 +275,7 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
                      uint8_t *out, int64_t out_pitch, int64_t out_stride,
                      int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st)
 {
-    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0};
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0, 0};
     // fast marching kernel: needs 4-byte aligned rows and an image at least as large as its reflect reach
     const bool fast_ok = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
                          !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
@@ -327,15 +328,26 @@ int launch_gray_blur_min_radius(const uint8_t *in, int64_t in_pitch, int64_t in_
 {
     if (!sigma) return B200MRC_OK;
     if (rmin != 3) return B200MRC_ERR_UNSUPPORTED;
-    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0};
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 5, rmin};
+    const bool fast_ok = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
+                         !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
+    if (!fast_ok) return B200MRC_ERR_ALIGNMENT;
+    {
+        // radius 3..4: the register-window marching kernel (pages of any other radius leave at once)
+        dim3 grid(cdiv(W, 120), cdiv(cdiv(H, FB_BAND), 8), N);
+        { ProfScope _ps("k_gray_blur_fast<3..4>", st);
+          if (C == 1) k_gray_blur_fast<1, 4><<<grid, 256, 0, st>>>(p);
+          else k_gray_blur_fast<3, 6><<<grid, 256, 0, st>>>(p); }
+        B200MRC_LAUNCH_CHECK();
+    }
     {
         constexpr int TH = 32, TW = 128, RHI = 16;
         constexpr size_t smem = gray_blur_smem<RHI, TH, TW>();
-        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<3, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200MRC_CUDA_TRY(cudaFuncSetAttribute(k_gray_blur_large<5, RHI, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int tiles = cdiv(W, TW) * cdiv(H, TH);
         int grid = dev_info().sm_count * 4;
         if (grid > tiles) grid = tiles;
-        { ProfScope _ps("k_gray_blur_large<3..16>", st); k_gray_blur_large<3, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
+        { ProfScope _ps("k_gray_blur_large<5..16>", st); k_gray_blur_large<5, RHI, TH, TW><<<grid, 256, smem, st>>>(p, N); }
         B200MRC_LAUNCH_CHECK();
     }
     {

@@ -40,6 +40,7 @@ namespace {
 constexpr int SK8 = 8;            // columns per thread
 constexpr int NS = 4;             // TMA stages (source rows in flight)
 constexpr int MAXR = 2;           // largest blur radius produced in-kernel
+constexpr int ETAB_SLOTS = 40;    // clamped-window output threads per CTA (2 page edges x ceil(128 / 8) columns, with slack)
 constexpr int STAGE_PAD = 16;     // bytes in front of / behind a staged row (neighbour reads of the CTA's edge lanes)
 constexpr unsigned FULLM = 0xffffffffu;
 
@@ -55,7 +56,7 @@ struct FusedParams {
     double km1, k2;
     int flags;
     int out8;                                                   // out rows allow 8-byte stores
-    int dbg;                                                    // FUSED_DBG: timing experiments only (results wrong): 1 no test, 2 no blur, 4 no scan/publish, 8 no slide, 16 no row barrier
+    int dbg;                                                    // FUSED_DBG = 1: skip the per-pixel test (timing experiments only; the mask is wrong)
     // byte offsets, inside one prefix buffer and relative to the thread's slot, of the entries a thread publishes
     // (st) and of the two window-edge entries of each of its 8 pixels (hi, lo): uniform values, so the shared-memory
     // accesses take them from the uniform register file
@@ -64,7 +65,7 @@ struct FusedParams {
 
 // smem carve-up (bytes), nt = threads per CTA
 struct FusedSmem {
-    int off_rowbar, off_wt, off_my, off_mx, off_p, off_stage, stage_stride, pbuf_bytes, total;
+    int off_rowbar, off_wt, off_my, off_mx, off_etab, off_p, off_stage, stage_stride, pbuf_bytes, total;
     __host__ __device__ FusedSmem(int nt, int C, int eb)
     {
         const int ncols = nt * SK8;
@@ -73,7 +74,8 @@ struct FusedSmem {
         off_wt = 256;                                   // [2][8] uint2 warp totals
         off_my = off_wt + 2 * 8 * 8;                    // [256] uint2: magic of n = ww * ny
         off_mx = off_my + 256 * 8;                      // [256] uint2: magic of n = nx * wh
-        off_p = off_mx + 256 * 8;                       // [3][8][sps] uint2 prefix of the column sums
+        off_etab = off_mx + 256 * 8;                    // [ETAB_SLOTS][8] uint2 + counter: per-pixel magics of clamped-window threads
+        off_p = off_etab + ETAB_SLOTS * 64 + 16;        // [3][8][sps] uint2 prefix of the column sums
         pbuf_bytes = 8 * sps * 8;
         off_stage = (off_p + 3 * pbuf_bytes + 127) & ~127;      // [NS][stage_stride]
         stage_stride = (ncols * C + 2 * STAGE_PAD + 15) & ~15;
@@ -118,7 +120,7 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
 //   E  slide the window: + gray row rc, - gray row y+2-o (delay line)
 template <int CS, int R, bool PRODUCE>
 __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem, const uint8_t *src, int64_t src_pitch,
-                                            uint8_t *gray, uint8_t *out, const double *sw)
+                                            uint8_t *gray, uint8_t *out, const double *sw, const int item)
 {
     static_assert(PRODUCE || (CS == 1 && R == 0), "direct mode reads a gray plane");
     constexpr int NE = SK8 + 2 * R;                  // columns of the vertical pass
@@ -133,7 +135,7 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     const int stage_stride = (ncols * CS + 2 * STAGE_PAD + 15) & ~15;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
+    const int strip = item % p.n_strips, band = item / p.n_strips;
     const int W = p.W, H = p.H;
     const int sx0 = strip * p.strip_w;
     const int ex0 = sx0 - p.ext_left;                // first column of this CTA (multiple of 16, may be negative)
@@ -151,6 +153,9 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
         lmask[h] = (!lok || v <= 0) ? 0u : (v >= 4 ? 0xffffffffu : (1u << (8 * v)) - 1u);
     }
     const bool nx_uniform = gx - p.l + 1 >= 0 && gx + 7 + p.r + 1 <= W;     // window width ww for all 8 pixels
+    // clamped-window threads keep the (magic, shift) of their 8 pixels' areas nx * wh in a small smem table
+    bool edge_ok = false;
+    const uint8_t *edge_tab = nullptr;
     const bool edge_l = R > 0 && gx == 0;                                     // blur taps left of the page: scipy 'reflect'
     const bool edge_r = R > 0 && lok && gx + 7 + R >= W;                      // blur taps right of the page
 
@@ -165,7 +170,8 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     const int rs_first = g0 - R, rs_last = rs_first + n_it - 1;
     auto issue_row = [&](int rs, int s) {
         mbar_expect_tx(&mbar[s], copy_bytes);
-        tma_load(stage + s * stage_stride + dst_off, src_col + (int64_t)reflect_idx(rs, H) * src_pitch, copy_bytes, &mbar[s]);
+        const int rr = rs < 0 ? -1 - rs : (rs >= H ? 2 * H - 1 - rs : rs);      // scipy 'reflect'; |overshoot| <= window/2 + 3 < H
+        tma_load(stage + s * stage_stride + dst_off, src_col + (int64_t)min(max(rr, 0), H - 1) * src_pitch, copy_bytes, &mbar[s]);
     };
     if (tid == 0) {
         mbar_init(rowbar, nt >> 5);
@@ -197,7 +203,9 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
             d[0] = v.x; d[1] = v.y;
         }
     };
-    uint32_t cA[2] = {0, 0}, lA[2] = {0, 0}, cB[2] = {0, 0}, lB[2] = {0, 0};
+    // cA / lA: rows the current iteration consumes (pixels of the tested row y-1, row y+2-o leaving the window);
+    // cN / lN: the same for the next iteration, loaded at the TOP of this one so that a whole iteration hides the latency
+    uint32_t cA[2] = {0, 0}, lA[2] = {0, 0}, cN[2] = {0, 0}, lN[2] = {0, 0};
 
     const int it_main = (by0 - 1) - y_start;         // first main iteration (>= 2)
     int slot = 0, par = 0;
@@ -207,14 +215,49 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     uint8_t *orow = out + (int64_t)by0 * p.out_pitch + gx;                // next mask row to write
     uint8_t *grow = PRODUCE ? gray + (int64_t)g0 * p.gray_pitch + gx : nullptr;   // next delay-line row to write (row rc)
 
-    __syncthreads();                                 // barrier init + prefix zero entries visible
+    {
+        // one 64-byte slot per clamped-window output thread (at most 2 * ceil(128 / 8) + 2 of them per CTA)
+        uint2 *etab = reinterpret_cast<uint2 *>(smem + L.off_etab);
+        const bool need = is_out && !nx_uniform;
+        const unsigned bal = __ballot_sync(FULLM, need);
+        int *ecount = reinterpret_cast<int *>(smem + L.off_etab + ETAB_SLOTS * 64);
+        if (tid == 0) *ecount = 0;
+        __syncthreads();
+        int slot_e = -1;
+        if (need) {
+            int basee = 0;
+            if ((bal & ((1u << lane) - 1u)) == 0) basee = atomicAdd(ecount, __popc(bal));   // first needing lane of the warp
+            basee = __shfl_sync(bal, basee, __ffs(bal) - 1);
+            slot_e = basee + __popc(bal & ((1u << lane) - 1u));
+            if (slot_e < ETAB_SLOTS) {
+                bool ok = true;
+                for (int k = 0; k < SK8; k++) {
+                    const int x = gx + k;
+                    uint2 e = make_uint2(1u, 0u);                    // pixels beyond the page: any divisor (never stored)
+                    if (x < W) {
+                        e = sMX[min(W, x + p.r + 1) - max(0, x - p.l + 1)];
+                        ok = ok && e.x != 0u;
+                    }
+                    etab[slot_e * 8 + k] = e;
+                }
+                edge_ok = ok;
+                edge_tab = reinterpret_cast<const uint8_t *>(etab + slot_e * 8);
+            }
+        }
+    }
+    __syncthreads();                                 // barrier init + prefix zero entries + edge tables visible
 
     for (int it = 0; it < n_it; it++) {
         const int y = y_start + it;
         const bool main = it >= it_main;
+        if (it + 1 >= it_main && it + 1 < n_it) {            // the next iteration is a main one: its delay-line rows
+            cN[0] = 0; cN[1] = 0;
+            if (y >= by0) load_row(y, cN);
+            load_row(y + 3 - p.o, lN);
+        }
         // ================= B: scan of the column sums of row y+1
         uint32_t bs = 0, bq = 0;
-        if (main && !(p.dbg & 4)) {
+        if (main) {
             const uint32_t ts = ((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]));
             const uint32_t tq = ((cq[0] + cq[1]) + (cq[2] + cq[3])) + ((cq[4] + cq[5]) + (cq[6] + cq[7]));
             uint32_t ws = ts, wq = tq;
@@ -224,7 +267,7 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
             bs = ws - ts; bq = wq - tq;              // exclusive within the warp
         }
         __syncwarp();
-        if (lane == 0 && !(p.dbg & 16)) mbar_arrive_cta(rowbar);
+        if (lane == 0) mbar_arrive_cta(rowbar);
 
         // ================= A: source row -> gray row rc
         mbar_wait(&mbar[slot], (uint32_t)par);
@@ -251,7 +294,6 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
             gw[0] = a.x; gw[1] = a.y;
         }
         uint32_t G[2];
-        if (R > 0 && (p.dbg & 2)) { G[0] = gw[0]; G[1] = gw[1]; } else
         if constexpr (R > 0) {
             // neighbour columns: R to the left (from lane - 1), R to the right (from lane + 1)
             uint32_t left = __shfl_up_sync(FULLM, gw[1], 1), right = __shfl_down_sync(FULLM, gw[0], 1);
@@ -290,13 +332,15 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                 for (int j = 0; j < R; j++) vf[R - 1 - j] = vf[R + j];
             }
             if (edge_r) {
-                float tmp[NE];
+                // column W + j mirrors to W - 1 - j; only the R columns next to the page edge feed a valid output.
+                // d = index of column W in vf[] (1 .. NE - 1), unrolled so that every access is a register
+                const int d = W - gx + R;
 #pragma unroll
-                for (int e = 0; e < NE; e++) tmp[e] = vf[e];
-                const int kk = 2 * W - 1 - 2 * (gx - R);         // column c = gx - R + e mirrors to index kk - e
-#pragma unroll
-                for (int e = 0; e < NE; e++)
-                    if (gx - R + e >= W) vf[e] = tmp[min(max(kk - e, 0), NE - 1)];
+                for (int dd = 1; dd < NE; dd++)
+                    if (d == dd) {
+                        vf[dd] = vf[dd - 1];
+                        if (R > 1 && dd + 1 < NE && dd >= 2) vf[dd + 1] = vf[dd - 2];
+                    }
             }
             double ext[NE];
 #pragma unroll
@@ -348,34 +392,46 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                     const double lhs = __dmul_rn(t, t);
                     return (uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs);
                 };
-                auto test_slow = [&](const int k, const int n) -> uint32_t {
-                    // floor((a + 0.5) * (1/n)) == a / n exactly (sauvola.cu)
-                    const double rn = 1.0 / (double)n;
-                    const double md = floor(__dmul_rn(__dadd_rn((double)S[k], 0.5), rn));
-                    const double qd = floor(__dmul_rn(__dadd_rn((double)Q[k], 0.5), rn));
-                    const double mm = __dmul_rn(md, md);
-                    const double vd = __dadd_rn(qd, -mm);
-                    const double pd = (double)byte_of(cA[k >> 2], k & 3);
-                    const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
-                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
-                    const double lhs = __dmul_rn(t, t);
-                    return (uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs);
-                };
                 uint32_t bits[2] = {0, 0};
-                if (nx_uniform && magicM != 0u) {
-                    // interior columns: one window area per row
+                // (magic, shift) of every pixel's window area: interior columns share the row's entry sMY[ny] (stride 0);
+                // columns whose window the page clamps have their own row-invariant entries sMX[nx] (interior rows)
+                const bool area_by_table = nx_uniform ? magicM != 0u : (ny == p.wh && edge_ok);
+                const unsigned act = __activemask();
+                if (__all_sync(act, nx_uniform && magicM != 0u)) {
+                    // the common warp: one window area per row for every pixel
 #pragma unroll
                     for (int k = 0; k < SK8; k++) bits[k >> 2] |= test_fast(k, magicM, magicS) << (8 * (k & 3));
-                } else {
-                    // columns whose window is clamped by the page: per-pixel area; interior rows still divide by table
+                } else if (__all_sync(act, area_by_table)) {
+                    // a warp at the left / right page edge: per-pixel areas through a pointer (stride 0 for its interior threads)
+                    const uint8_t *mp = nx_uniform ? reinterpret_cast<const uint8_t *>(sMY + ny) : edge_tab;
+                    const int mstride = nx_uniform ? 0 : 8;
 #pragma unroll
+                    for (int k = 0; k < SK8; k++) {
+                        const uint2 mg = *reinterpret_cast<const uint2 *>(mp + k * mstride);
+                        bits[k >> 2] |= test_fast(k, mg.x, mg.y) << (8 * (k & 3));
+                    }
+                } else {
+                    // page corners (clamped in both directions), windows too large for the 32-bit magic, pixels beyond the
+                    // right page edge: per-pixel area, FP64 quotient floor((a + 0.5) * (1/n)) == a / n (sauvola.cu)
+#pragma unroll 1
                     for (int k = 0; k < SK8; k++) {
                         const int x = gx + k;
                         const int nx = (x < W) ? min(W, x + p.r + 1) - max(0, x - p.l + 1) : 0;
-                        if (nx > 0) {
-                            const uint2 mg = (ny == p.wh) ? sMX[nx] : make_uint2(0u, 0u);
-                            const uint32_t fg = mg.x ? test_fast(k, mg.x, mg.y) : test_slow(k, nx * ny);
-                            bits[k >> 2] |= fg << (8 * (k & 3));
+                        const int n = nx * ny;
+                        if (n > 0) {
+                            const uint2 hi = *reinterpret_cast<const uint2 *>(P + p.bo_hi[k]);
+                            const uint2 lo = *reinterpret_cast<const uint2 *>(P + p.bo_lo[k]);
+                            const double rn = 1.0 / (double)n;
+                            const double md = floor(__dmul_rn(__dadd_rn((double)(hi.x - lo.x), 0.5), rn));
+                            const double qd = floor(__dmul_rn(__dadd_rn((double)(hi.y - lo.y), 0.5), rn));
+                            const double mm = __dmul_rn(md, md);
+                            const double vd = __dadd_rn(qd, -mm);
+                            const double pd = (double)(((k < 4 ? cA[0] : cA[1]) >> (8 * (k & 3))) & 0xffu);
+                            const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
+                            const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
+                            const double lhs = __dmul_rn(t, t);
+                            const uint32_t fgb = ((uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs)) << (8 * (k & 3));
+                            if (k < 4) bits[0] |= fgb; else bits[1] |= fgb;
                         }
                     }
                 }
@@ -402,14 +458,12 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
         }
 
         // ================= WAIT: every warp has published its total of row y+1 (and is done with the previous stage)
-        if (!(p.dbg & 16)) mbar_wait(rowbar, (uint32_t)(it & 1)); else __syncthreads();
+        mbar_wait(rowbar, (uint32_t)(it & 1));
         if (tid == 0 && it > 0) {
             const int rs = rs_first + (it - 1) + NS;                 // refill the stage every thread read in iteration it-1
             if (rs <= rs_last) issue_row(rs, slot == 0 ? NS - 1 : slot - 1);
         }
-        if (main && (p.dbg & 4)) { const int t_ = o_test; o_test = o_mid; o_mid = o_pub; o_pub = t_; }
-        if (main && (p.dbg & 8)) { cA[0] = cB[0]; cA[1] = cB[1]; cs[0] += G[0]; }
-        if (main && !(p.dbg & 12)) {
+        if (main) {
             // ================= C: CTA-wide prefix of the column sums of row y+1 -> ring buffer o_pub
             uint32_t as = bs, aq = bq;
             const uint2 *T = sWT + (it & 1) * 8;
@@ -428,9 +482,6 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                 cs[k] += a - b;
                 cq[k] += a * a - b * b;
             }
-            cA[0] = cB[0]; cA[1] = cB[1]; lA[0] = lB[0]; lA[1] = lB[1];
-            if (y + 1 < by1) load_row(y + 1, cB);
-            if (y + 2 < by1) load_row(y + 4 - p.o, lB);
             const int t_ = o_test; o_test = o_mid; o_mid = o_pub; o_pub = t_;
         } else {
             // warm-up: gray row rc joins the window of the band's first row
@@ -439,12 +490,8 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                 const uint32_t a = byte_of(G[k >> 2], k & 3);
                 cs[k] += a; cq[k] += a * a;
             }
-            if (it + 1 == it_main) {
-                // the delay line now holds every row the first two main iterations subtract
-                load_row(by0 + 1 - p.o, lA);
-                load_row(by0 + 2 - p.o, lB);
-            }
         }
+        cA[0] = cN[0]; cA[1] = cN[1]; lA[0] = lN[0]; lA[1] = lN[1];
         if (++slot == NS) { slot = 0; par ^= 1; }
     }
 }
@@ -456,7 +503,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sauvola_fused(const FusedParams 
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     double *sw = reinterpret_cast<double *>(smem + 64);          // 3 weights
     double *sphi = sw + 4;                                       // 5 scratch
-    const int page = blockIdx.y;
+    // grid: x = (band, strip) of a page, y = page.  (Placing the CTAs of one page -- one blur radius, one code variant -- on
+    // the same SMs was tried and is slower for batches of mixed radii: the SMs holding the heavier variant finish last.)
+    const int page = blockIdx.y, item = blockIdx.x;
     const int tid = threadIdx.x;
     const FusedSmem L(blockDim.x, C, p.eb);
 
@@ -498,15 +547,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sauvola_fused(const FusedParams 
     uint8_t *gray = p.gray ? p.gray + (int64_t)page * p.gray_stride : nullptr;
     uint8_t *out = p.out + (int64_t)page * p.out_stride;
     if (radius > MAXR) {
-        fused_march<1, 0, false>(p, smem, gray, p.gray_pitch, nullptr, out, sw);      // pre-blurred by gray_blur.cu
+        fused_march<1, 0, false>(p, smem, gray, p.gray_pitch, nullptr, out, sw, item);      // pre-blurred by gray_blur.cu
     } else if (C == 3) {
-        if (radius == 0) fused_march<3, 0, true>(p, smem, src, p.src_pitch, gray, out, sw);
-        else if (radius == 1) fused_march<3, 1, true>(p, smem, src, p.src_pitch, gray, out, sw);
-        else fused_march<3, 2, true>(p, smem, src, p.src_pitch, gray, out, sw);
+        if (radius == 0) fused_march<3, 0, true>(p, smem, src, p.src_pitch, gray, out, sw, item);
+        else if (radius == 1) fused_march<3, 1, true>(p, smem, src, p.src_pitch, gray, out, sw, item);
+        else fused_march<3, 2, true>(p, smem, src, p.src_pitch, gray, out, sw, item);
     } else {
-        if (radius == 0) fused_march<1, 0, false>(p, smem, src, p.src_pitch, nullptr, out, sw);
-        else if (radius == 1) fused_march<1, 1, true>(p, smem, src, p.src_pitch, gray, out, sw);
-        else fused_march<1, 2, true>(p, smem, src, p.src_pitch, gray, out, sw);
+        if (radius == 0) fused_march<1, 0, false>(p, smem, src, p.src_pitch, nullptr, out, sw, item);
+        else if (radius == 1) fused_march<1, 1, true>(p, smem, src, p.src_pitch, gray, out, sw, item);
+        else fused_march<1, 2, true>(p, smem, src, p.src_pitch, gray, out, sw, item);
     }
 }
 
@@ -618,11 +667,11 @@ namespace b200mrc {
 int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int C,
                      uint8_t *out, int64_t out_pitch, int64_t out_stride,
                      int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st);
-// Tuning key THRESHOLD_PATH: fused (one kernel, sauvola_fused.cu) or legacy (gray_blur.cu + sauvola.cu).  Measured on B200
-// (profiles/r2_fused_threshold.md): the fused kernel moves half the bytes and executes 18 % fewer instructions, but its 96-128
-// registers per thread hold it at 16-20 warps per SM and 0.47 IPC, against 32-48 warps and 0.7 IPC for the two lean
-// kernels -- 4.7 ms against 3.5 ms for 64 RGB pages.  auto therefore picks the two-pass form.
-bool threshold_path_legacy() { return tune(T_THRESHOLD_PATH) != 2; }
+// Tuning key THRESHOLD_PATH: auto / fused (one kernel, this file) or legacy (gray_blur.cu + sauvola.cu).  Measured on B200,
+// 64 RGB pages 3300x2550, window 101 (profiles/r2_threshold_paths.txt): fused 2.4 / 3.3 / 3.9 ms for blur radius 0 / 1 / 2
+// against 3.0 / 3.5 / 3.8 ms for the two kernels; batches that mix radii favour the two-pass form by ~15 % (the fused
+// kernel runs as one wave, so its slowest CTA sets the time).  auto picks the fused kernel wherever it applies.
+bool threshold_path_legacy() { return tune(T_THRESHOLD_PATH) == 1; }
 }  // namespace b200mrc
 
 extern "C" size_t b200mrc_threshold_workspace_bytes(int width, int height, int n_pages)

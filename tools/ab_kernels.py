@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--gray', action='store_true')
     ap.add_argument('--mask-only', action='store_true')
     ap.add_argument('--halftone', action='store_true')
+    ap.add_argument('--sigma-n', type=float, default=3.0, help='sensor noise of the synthetic pages (decides the blur radius)')
     ap.add_argument('--call', choices=['decompose', 'staged'], default='decompose',
                     help='decompose: one b200mrc_decompose per step (page groups on internal streams); staged: one C-ABI call per stage')
     ap.add_argument('variants', nargs='*', default=['{}'])
@@ -34,7 +35,7 @@ def main():
     H, W = a.shape
     C = 1 if a.gray else 3
     window = pkg.window_for_dpi(a.dpi)
-    distinct = [synth.make_page(i, H, W, dpi=a.dpi, rgb=not a.gray, halftone=a.halftone and i % 3 == 0) for i in range(a.distinct)]
+    distinct = [synth.make_page(i, H, W, dpi=a.dpi, rgb=not a.gray, sigma_n=a.sigma_n, halftone=a.halftone and i % 3 == 0) for i in range(a.distinct)]
     eng = pkg.get_engine()
     for npages in [int(v) for v in a.pages.split(',')]:
         pages = np.stack([distinct[i % a.distinct] for i in range(npages)])
