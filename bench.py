@@ -330,6 +330,7 @@ def main():
     ap.add_argument('--config', type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pipelined', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the short runs of configs 3, 4, 5 in the default line')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
@@ -393,6 +394,38 @@ def main():
     if not cfg['sauvola_only']:
         kernel_ms, serial_ms = serialized_kernel_table(run, _lib)
 
+    # ---- the same K steps with two batches in flight (one CUDA stream per in-flight batch: a book is a stream of batches):
+    # the row-latency-bound sweep of one batch overlaps the issue-bound stages of the next.  Reported next to `value`,
+    # which stays the plain one-call-at-a-time figure.
+    pipelined = None
+    if not args.no_pipelined and not cfg['sauvola_only']:
+        batch2 = run.eng.make_batch(N, H, W, C, bg_downsample=cfg['bg'], mask_only=cfg['mask_only'])
+        batch2.img = run.batch.img                      # same resident input pages, private outputs / workspace
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        both = [run.batch, batch2]
+
+        def pipelined_steps(k):
+            cur = torch.cuda.current_stream()
+            for s_ in streams:
+                s_.wait_stream(cur)
+            for i in range(k):
+                with torch.cuda.stream(streams[i % 2]):
+                    both[i % 2].run(cfg['window'], denoise_mask='fast')
+            for s_ in streams:
+                cur.wait_stream(s_)
+
+        pipelined_steps(4)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pipelined_steps(args.steps)
+        p1.record()
+        barrier()
+        pt = max_ranks(p0.elapsed_time(p1))
+        pipelined = {'value': px_step * args.steps / (pt / 1e3) / 1e6, 'unit': 'Mpixels/s', 'ms_per_step': pt / args.steps,
+                     'batches_in_flight': 2}
+        del batch2, both
+
     # ---- end to end through the public host API: pinned host pages -> results in pinned host memory
     e2e = None
     if not args.no_e2e and not cfg['sauvola_only']:
@@ -403,78 +436,85 @@ def main():
         e2e_chunk = int(os.environ.get('B200MRC_E2E_CHUNK', '4' if H * W * C > 2e7 else ('8' if C == 3 else '16')))
         e2e_streams = int(os.environ.get('B200MRC_E2E_STREAMS', '2'))
         e2e_buffers = int(os.environ.get('B200MRC_E2E_BUFFERS', '4'))
-        e2e_packed = os.environ.get('B200MRC_E2E_PACKED_MASK', '0') == '1'
-        sd = StreamedDecomposer(run.eng, N, H, W, C, chunk=e2e_chunk, bg_downsample=cfg['bg'], buffers=e2e_buffers,
-                                compute_streams=e2e_streams, mask_only=cfg['mask_only'], packed_mask=e2e_packed)
-        # a book is a stream of batches: two batches in flight (each with its own pinned result buffers), so the H2D
-        # copies and kernels of step i+1 overlap the D2H tail of step i; every step's inputs cross PCIe and every
-        # step's results are waited for and read on the host inside the timed region
-        outs2 = [sd.alloc_outputs() for _ in range(2)]
         last = 'mask' if cfg['mask_only'] else 'bg'
 
-        def e2e_run(steps, depth):
-            pending = []
-            seen = 0
-            for i in range(steps):
-                o = outs2[i % 2]
-                pending.append((sd.run_async(host, o, cfg['window'], denoise_mask='fast'), o))
-                if len(pending) >= depth:
-                    ev, oo = pending.pop(0)
-                    ev.synchronize()                              # the results of that step are in pinned host memory
+        def measure_e2e(packed):
+            sd = StreamedDecomposer(run.eng, N, H, W, C, chunk=e2e_chunk, bg_downsample=cfg['bg'], buffers=e2e_buffers,
+                                    compute_streams=e2e_streams, mask_only=cfg['mask_only'], packed_mask=packed)
+            # a book is a stream of batches: two batches in flight (each with its own pinned result buffers), so the H2D
+            # copies and kernels of step i+1 overlap the D2H tail of step i; every step's inputs cross PCIe and every
+            # step's results are waited for and read on the host inside the timed region
+            outs2 = [sd.alloc_outputs() for _ in range(2)]
+
+            def e2e_run(steps, depth):
+                pending = []
+                seen = 0
+                for i in range(steps):
+                    o = outs2[i % 2]
+                    pending.append((sd.run_async(host, o, cfg['window'], denoise_mask='fast'), o))
+                    if len(pending) >= depth:
+                        ev, oo = pending.pop(0)
+                        ev.synchronize()                          # the results of that step are in pinned host memory
+                        seen += int(oo['mask'][0, 0, 0]) + int(oo[last][-1, -1, -1])
+                for ev, oo in pending:
+                    ev.synchronize()
                     seen += int(oo['mask'][0, 0, 0]) + int(oo[last][-1, -1, -1])
-            for ev, oo in pending:
-                ev.synchronize()
-                seen += int(oo['mask'][0, 0, 0]) + int(oo[last][-1, -1, -1])
-            return seen
+                return seen
 
-        e2e_run(2, 2)
-        e2e_steps = max(3, min(args.steps, 10))
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.time()
-        e2e_run(e2e_steps, 1)                                     # one call at a time (run() semantics)
-        torch.cuda.synchronize()
-        barrier()
-        dt_sync = max_ranks(time.time() - t0)
-        t0 = time.time()
-        e2e_run(e2e_steps, 2)
-        torch.cuda.synchronize()
-        barrier()
-        dt = max_ranks(time.time() - t0)
-        # the platform ceiling of exactly this transfer pattern: every step's H2D and D2H bytes, both directions at once,
-        # all ranks concurrently, no kernels (what the host<->device path of this box can deliver at N GPUs)
-        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-        dev_in = torch.empty_like(host, device='cuda')
-        dev_out = {k: torch.empty_like(v, device='cuda') for k, v in outs2[0].items()}
+            e2e_run(2, 2)
+            e2e_steps = max(3, min(args.steps, 10))
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.time()
+            e2e_run(e2e_steps, 1)                                 # one call at a time (run() semantics)
+            torch.cuda.synchronize()
+            barrier()
+            dt_sync = max_ranks(time.time() - t0)
+            t0 = time.time()
+            e2e_run(e2e_steps, 2)
+            torch.cuda.synchronize()
+            barrier()
+            dt = max_ranks(time.time() - t0)
+            # the platform ceiling of exactly this transfer pattern: every step's H2D and D2H bytes, both directions at
+            # once, all ranks concurrently, no kernels (what the host<->device path of this box can deliver at N GPUs)
+            s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            dev_in = torch.empty_like(host, device='cuda')
+            dev_out = {k: torch.empty_like(v, device='cuda') for k, v in outs2[0].items()}
 
-        def copy_only():
-            with torch.cuda.stream(s_h2d):
-                dev_in.copy_(host, non_blocking=True)
-            with torch.cuda.stream(s_d2h):
-                for k, v in outs2[0].items():
-                    v.copy_(dev_out[k], non_blocking=True)
+            def copy_only():
+                with torch.cuda.stream(s_h2d):
+                    dev_in.copy_(host, non_blocking=True)
+                with torch.cuda.stream(s_d2h):
+                    for k, v in outs2[0].items():
+                        v.copy_(dev_out[k], non_blocking=True)
 
-        copy_only(); torch.cuda.synchronize(); barrier()
-        t0 = time.time()
-        for _ in range(3):
-            copy_only()
-        torch.cuda.synchronize()
-        barrier()
-        dt_copy = max_ranks((time.time() - t0) / 3)
-        del dev_in, dev_out
-        e2e = {'value': px_step * e2e_steps / dt / 1e6, 'unit': 'Mpixels/s', 'steps': e2e_steps,
-               'copy_only_ms_per_step': dt_copy * 1e3, 'ms_per_step': dt / e2e_steps * 1e3,
-               'frac_of_copy_ceiling': dt_copy / (dt / e2e_steps),
-               'copy_ceiling_note': 'copy_only = the same H2D + D2H bytes per step on two streams, no kernels, all ranks at once: the '
-                                    'host<->device ceiling of this box at this N; frac = copy_only time / e2e step time',
-               'h2d_bytes_per_step': int(host.numel()) * world,
-               'd2h_bytes_per_step': int(sum(v.numel() for v in outs2[0].values())) * world,
-               'one_call_at_a_time': px_step * e2e_steps / dt_sync / 1e6, 'batches_in_flight': 2, 'packed_mask': e2e_packed,
-               'api': 'archive_pdf_tools_b200.engine.StreamedDecomposer.run_async: pinned host pages -> 1-D H2D DMA -> device pitching '
+            copy_only(); torch.cuda.synchronize(); barrier()
+            t0 = time.time()
+            for _ in range(3):
+                copy_only()
+            torch.cuda.synchronize()
+            barrier()
+            dt_copy = max_ranks((time.time() - t0) / 3)
+            res = {'value': px_step * e2e_steps / dt / 1e6, 'unit': 'Mpixels/s', 'steps': e2e_steps,
+                   'ms_per_step': dt / e2e_steps * 1e3, 'copy_only_ms_per_step': dt_copy * 1e3,
+                   'frac_of_copy_ceiling': dt_copy / (dt / e2e_steps),
+                   'h2d_bytes_per_step': int(host.numel()) * world,
+                   'd2h_bytes_per_step': int(sum(v.numel() for v in outs2[0].values())) * world,
+                   'one_call_at_a_time': px_step * e2e_steps / dt_sync / 1e6, 'batches_in_flight': 2, 'packed_mask': packed}
+            del sd, outs2, dev_in, dev_out
+            torch.cuda.empty_cache()
+            return res
+
+        e2e = measure_e2e(False)
+        e2e['copy_ceiling_note'] = ('copy_only = the same H2D + D2H bytes per step on two streams, no kernels, all ranks at once: the '
+                                    'host<->device ceiling of this box at this N; frac = copy_only time / e2e step time')
+        e2e['api'] = ('archive_pdf_tools_b200.engine.StreamedDecomposer.run_async: pinned host pages -> 1-D H2D DMA -> device pitching '
                       '(b200mrc_copy2d) -> b200mrc_decompose (%d-page chunks, %d compute streams, %d device buffers) -> device '
-                      'unpitching -> 1-D D2H DMA of mask/fg/bg into pinned host buffers' % (e2e_chunk, e2e_streams, e2e_buffers)}
-        del sd, outs2
-        torch.cuda.empty_cache()
+                      'unpitching -> 1-D D2H DMA of mask/fg/bg into pinned host buffers' % (e2e_chunk, e2e_streams, e2e_buffers))
+        # the same path handing the mask over as PIL mode-'1' rows (b200mrc_pack_mask: what encode_mrc_mask, mrc.py:474-520,
+        # builds from the bool array anyway): 8x fewer mask bytes over PCIe.  Reported separately: `value` above returns the
+        # reference's own bool plane.
+        e2e['packed_mask_variant'] = measure_e2e(True)
 
     # ---- short runs of the other BASELINE configs (default line only)
     extra = None
@@ -542,7 +582,7 @@ def main():
         'dtype': 'u8', 'data': 'synthetic (%d distinct pages per GPU tiled to %d)' % (cfg['distinct'], N),
         'config': bench_config(cfg, world, page_groups=_lib.get_tuning('DECOMPOSE_GROUPS') or 'auto'),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-        'extra_configs': extra,
+        'pipelined': pipelined, 'extra_configs': extra,
     }
     print(json.dumps(line))
     return 0
