@@ -461,9 +461,9 @@ class StreamedDecomposer:
                 for name in names:
                     plane, st = getattr(b, name), self.st_out[slot][name]
                     if name == 'mask' and self.packed_mask:
-                        nb = (plane.w + 7) // 8
-                        L.check(L.lib().b200mrc_pack_mask(plane.ptr, plane.pitch, plane.page_stride, C.c_void_p(st.data_ptr()), nb,
-                                                          plane.h * nb, plane.w, plane.h, m, 0, C.c_void_p(sc.cuda_stream)),
+                        row_b = (plane.w + 7) // 8
+                        L.check(L.lib().b200mrc_pack_mask(plane.ptr, plane.pitch, plane.page_stride, C.c_void_p(st.data_ptr()), row_b,
+                                                          plane.h * row_b, plane.w, plane.h, m, 0, C.c_void_p(sc.cuda_stream)),
                                 'b200mrc_pack_mask')
                     elif st is not None:
                         row = plane.w * plane.c

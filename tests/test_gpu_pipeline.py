@@ -426,13 +426,13 @@ def test_streamed_decomposer_packed_mask(eng, synth):
     import torch
     import archive_pdf_tools_b200 as pkg
     from archive_pdf_tools_b200.engine import StreamedDecomposer
-    pages = np.stack([synth.make_page(400 + i, 130, 203, dpi=100) for i in range(5)])
+    pages = np.stack([synth.make_page(400 + i, 130, 203, dpi=100) for i in range(11)])
     ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
     host = torch.from_numpy(pages).pin_memory()
-    sd = StreamedDecomposer(eng, 5, 130, 203, 3, chunk=2, bg_downsample=3, packed_mask=True)
+    sd = StreamedDecomposer(eng, 11, 130, 203, 3, chunk=2, buffers=2, bg_downsample=3, packed_mask=True)   # more chunks than buffers
     out = sd.alloc_outputs()
     sd.run(host, out, 25, denoise_mask='fast')
-    assert out['mask'].shape == (5, 130, (203 + 7) // 8)
+    assert out['mask'].shape == (11, 130, (203 + 7) // 8)
     assert np.array_equal(out['mask'].numpy(), np.packbits(ref['mask'], axis=-1))
     assert np.array_equal(out['fg'].numpy().reshape(ref['fg'].shape), ref['fg'])
     assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small driver for ncu: runs the staged pipeline on N synthetic 400-DPI pages (see bench.py).
+"""Small driver for ncu: runs b200mrc_decompose (one call per step) on N synthetic 400-DPI pages (see bench.py).
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \\
         python tools/profile_step.py --pages 64 --steps 2 --warmup 1
 """
@@ -31,7 +31,7 @@ def main():
     batch = eng.make_batch(a.pages, H, W, 3, bg_downsample=3, mask_only=a.mask_only)
     batch.img.upload(pages, non_blocking=False)
     for _ in range(a.warmup + a.steps):
-        batch.run_staged(101, denoise_mask='fast')
+        batch.run(101, denoise_mask='fast')
     torch.cuda.synchronize()
     print('done', float(batch.sigma.cpu()[0]))
 
