@@ -131,8 +131,8 @@ GroupPlan group_plan(int N)
     const int env_groups = tune(T_DECOMPOSE_GROUPS), env_streams = tune(T_DECOMPOSE_STREAMS);
     // measured (profiles/r2_ab_groups.txt): the sweep is row-latency bound, so its time hardly depends on the number of pages;
     // splitting a 64-page batch multiplies that time and overlap does not win it back.  Groups pay off only when each
-    // of them still fills the machine.
-    int g = env_groups > 0 ? env_groups : (N >= 192 ? 2 : 1);
+    // of them still fills the machine -- and even 2 x 128 small gray pages ran 10 % slower than one group of 256.
+    int g = env_groups > 0 ? env_groups : 1;
     if (g > N) g = N;
     GroupPlan gp;
     gp.per_group = (N + g - 1) / g;
