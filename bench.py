@@ -554,7 +554,7 @@ def main():
     per_kernel = {}
     for k, ms in kernel_ms.items():
         base = k.split('<')[0]
-        ab = alg.get(base)
+        ab = alg.get(base) if ms >= 0.05 else None           # launches that only skip pages (other blur radii) move no bytes
         per_kernel[k] = {'ms': ms, 'alg_bytes': ab * run_px(cfg) if ab else None,
                          'frac': (ab * run_px(cfg) / (ms / 1e3) / 1e9 / peak) if ab and ms > 0 else None,
                          'dram_bytes': traffic.get(base)}
