@@ -61,6 +61,7 @@ const TuneDef k_tune_defs[T_COUNT] = {
     {"THRESHOLD_PATH", 0, "legacy", "fused"}, {"OPT_PATH", 0, "generic", nullptr}, {"NOISE_DIRECT", 0, nullptr, nullptr},
     {"RESAMPLE_2PASS", 0, nullptr, nullptr}, {"TILE_H", 32, nullptr, nullptr}, {"DECOMPOSE_GROUPS", 0, nullptr, nullptr},
     {"DECOMPOSE_STREAMS", 0, nullptr, nullptr},
+    {"BG_FOLLOW", 1, nullptr, nullptr},
 };
 std::atomic<int> g_tune[T_COUNT];
 std::once_flag g_tune_once;
@@ -116,7 +117,10 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                     const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                     uint8_t *ofg, int64_t fpitch, int64_t fstride, int nfg,
                     uint8_t *obg, int64_t bpitch, int64_t bstride, int nbg,
-                    int W, int H, int N, void *workspace, size_t workspace_bytes, cudaStream_t st);
+                    int W, int H, int N, void *workspace, size_t workspace_bytes, cudaStream_t st, int **bg_progress);
+int launch_resample_follow(const b200mrc_resample_plan *pl, const uint8_t *in, int64_t in_pitch, int64_t in_page_stride,
+                           uint8_t *out, int64_t out_pitch, int64_t out_page_stride, int n_pages,
+                           const int *prog, int prog_s, int prog_w, cudaStream_t st);
 
 namespace {
 
@@ -269,14 +273,25 @@ int decompose_group(const b200mrc_decompose_args *a, const DecomposeLayout &L, i
     uint8_t *bg_full = a->bg_plan ? ws + L.off_bgfull + (size_t)p0 * L.full_page : bg_out;
     const int64_t fgp = a->fg_plan ? (int64_t)L.full_pitch : a->fg_pitch, fgs = a->fg_plan ? (int64_t)L.full_page : a->fg_page_stride;
     const int64_t bgp = a->bg_plan ? (int64_t)L.full_pitch : a->bg_pitch, bgs = a->bg_plan ? (int64_t)L.full_page : a->bg_page_stride;
+    // tuning key BG_FOLLOW (default on): the bg thumbnail runs as a follower of the sweep
+    const bool follow = a->bg_plan && tune(T_BG_FOLLOW) != 0;
+    int *bg_prog = nullptr;
+    bool bg_done = false;
     rc = launch_optimise(mask, a->mask_pitch, a->mask_page_stride, img, a->img_pitch, a->img_page_stride, C,
-                         fg_full, fgp, fgs, 3, bg_full, bgp, bgs, 10, W, H, n, ws + L.off_opt + (size_t)g * L.opt_bytes, L.opt_bytes, st);
+                         fg_full, fgp, fgs, 3, bg_full, bgp, bgs, 10, W, H, n, ws + L.off_opt + (size_t)g * L.opt_bytes, L.opt_bytes, st,
+                         follow ? &bg_prog : nullptr);
     if (rc) return rc;
+    if (bg_prog) {
+        // the thumbnail pass starts beside the sweep (its programmatic dependent) and consumes bg rows as strips publish them
+        rc = launch_resample_follow(a->bg_plan, bg_full, bgp, bgs, bg_out, a->bg_pitch, a->bg_page_stride, n, bg_prog, cdiv(W, 128), 128, st);
+        if (rc == B200MRC_OK) bg_done = true;
+        else if (rc != B200MRC_ERR_UNSUPPORTED) return rc;
+    }
     if (a->fg_plan) {
         rc = b200mrc_resample(a->fg_plan, fg_full, fgp, fgs, fg_out, a->fg_pitch, a->fg_page_stride, n, scratch, L.scratch_bytes, st);
         if (rc) return rc;
     }
-    if (a->bg_plan) {
+    if (a->bg_plan && !bg_done) {
         rc = b200mrc_resample(a->bg_plan, bg_full, bgp, bgs, bg_out, a->bg_pitch, a->bg_page_stride, n, scratch, L.scratch_bytes, st);
         if (rc) return rc;
     }

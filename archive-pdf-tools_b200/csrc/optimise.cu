@@ -302,7 +302,7 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                           const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                           uint8_t *ofg, int64_t fpitch, int64_t fstride,
                           uint8_t *obg, int64_t bpitch, int64_t bstride,
-                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, unsigned *ticket, cudaStream_t st);
+                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, unsigned *ticket, int *progress, cudaStream_t st);
 
 size_t optimise_workspace_bytes(int W, int H, int N) { return opt_layout(W, H, N).total; }
 
@@ -310,17 +310,23 @@ int launch_optimise(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                     const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                     uint8_t *ofg, int64_t fpitch, int64_t fstride, int nfg,
                     uint8_t *obg, int64_t bpitch, int64_t bstride, int nbg,
-                    int W, int H, int N, void *workspace, size_t workspace_bytes, cudaStream_t st)
+                    int W, int H, int N, void *workspace, size_t workspace_bytes, cudaStream_t st, int **bg_progress)
 {
+    // bg_progress (optional): on return *bg_progress is null, or a device array [N][cdiv(W, 128)] in which the sweep
+    // publishes, per 128-column strip, how many rows of `obg` are globally visible (release stores) -- a kernel launched
+    // behind the sweep as its programmatic dependent may consume bg rows while the sweep is still running (resample.cu)
+    if (bg_progress) *bg_progress = nullptr;
     const OptLayout L = opt_layout(W, H, N);
     if (!workspace || workspace_bytes < L.total) return B200MRC_ERR_WORKSPACE;
     uint8_t *ws = (uint8_t *)workspace;
     // tuning key OPT_PATH: split (default) | generic, A/B switch for profiling
     if (nfg == 3 && nbg == 10 && tune(T_OPT_PATH) == 0) {
         // production path: parallel FIR record plane + row-sequential warp-strip sweep (optimise_split.cu)
+        int *prog = bg_progress ? (int *)(ws + L.off_prog) : nullptr;
         const int frc = launch_optimise_split(mask, mpitch, mstride, img, ipitch, istride, C, ofg, fpitch, fstride,
                                               obg, bpitch, bstride, W, H, N, ws + L.off_rec, (uint32_t *)(ws + L.off_mailbox),
-                                              (unsigned *)(ws + L.off_ticket), st);
+                                              (unsigned *)(ws + L.off_ticket), prog, st);
+        if (frc == B200MRC_OK && bg_progress) *bg_progress = prog;
         if (frc != B200MRC_ERR_UNSUPPORTED) return frc;
     }
     OptPlan plan;
@@ -368,5 +374,5 @@ extern "C" int b200mrc_optimise(const uint8_t *mask, int64_t mask_pitch, int64_t
     if (n_fg < 1 || n_bg < 1 || n_fg > B200MRC_MAX_OPT_N || n_bg > B200MRC_MAX_OPT_N) return B200MRC_ERR_UNSUPPORTED;
     return launch_optimise(mask, mask_pitch, mask_page_stride, img, img_pitch, img_page_stride, channels,
                            out_fg, fg_pitch, fg_page_stride, n_fg, out_bg, bg_pitch, bg_page_stride, n_bg,
-                           width, height, n_pages, workspace, workspace_bytes, (cudaStream_t)stream);
+                           width, height, n_pages, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }

@@ -26,7 +26,7 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
                         const uint8_t *rec, int64_t rpitch, int64_t rstride,
                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
                         uint8_t *obg, int64_t bpitch, int64_t bstride,
-                        int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, cudaStream_t st);
+                        int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, int *progress, cudaStream_t st);
 
 // record plane: 8 B / pixel, rows padded to whole 4-pixel groups (the sweep reads whole groups)
 int64_t optimise_split_rec_pitch(int W) { return (int64_t)((W + 3) / 4 * 4) * 8; }
@@ -37,7 +37,7 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                           const uint8_t *img, int64_t ipitch, int64_t istride, int C,
                           uint8_t *ofg, int64_t fpitch, int64_t fstride,
                           uint8_t *obg, int64_t bpitch, int64_t bstride,
-                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, unsigned *ticket, cudaStream_t st)
+                          int W, int H, int N, uint8_t *rec, uint32_t *mailbox, unsigned *ticket, int *progress, cudaStream_t st)
 {
     auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
     const int64_t need_i = ((int64_t)W * C + 15) & ~15ll, need_m = ((int64_t)W + 15) & ~15ll;
@@ -53,7 +53,7 @@ int launch_optimise_split(const uint8_t *mask, int64_t mpitch, int64_t mstride,
                                  firw_band, firw_wpc, mailbox, cdiv(W, 128), st);
     if (rc != B200MRC_OK) return rc;
     return launch_opt_iir_warp(img, ipitch, istride, C, rec, rpitch, rstride, ofg, fpitch, fstride, obg, bpitch, bstride,
-                               W, H, N, mailbox, ticket, iirw_wpc, st);
+                               W, H, N, mailbox, ticket, iirw_wpc, progress, st);
 }
 
 }  // namespace b200mrc

@@ -56,6 +56,7 @@ struct IirWParams {
     unsigned *ticket;
     uint32_t tag;                       // epoch spread over TAGMASK
     unsigned psleep;                    // trio form: producer back-off (ns) when no stage is free
+    int *progress;                      // optional [N][S]: rows of the bg output of every strip that are globally visible (followers: resample.cu)
 };
 
 template <int C> struct WarpSmem {
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
     if (threadIdx.x == 0) Mtab[0] = 0;
     for (int i = lane; i < SM::bytes / 16; i += 32) reinterpret_cast<uint4 *>(wb)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();                                         // the only CTA-wide barrier
+    pdl_launch_dependents();                                 // a programmatic dependent (the bg thumbnail pass) may become resident beside this grid
 
     uint64_t *mbar = reinterpret_cast<uint64_t *>(wb + SM::off_mbar);
     uint8_t *rgbS = wb + SM::off_rgb, *recS = wb + SM::off_rec, *ost = wb + SM::off_ost;
@@ -395,6 +397,13 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
             tma_commit();
             if (y + IST < H) issue_row(y + IST, slot);       // every lane has read this stage (syncwarp above)
         }
+        if (p.progress && (y & 31) == 31 && lane == 0) {
+            // rows the followers of this sweep may read.  Bulk stores: all groups but the 8 newest have completed (no
+            // stall: they are long done), the release makes them visible.  Lanes' 16-byte stores: those of the rows
+            // before this one precede this row's warp barrier, hence lane 0's release.
+            if (ASYNC) st_release(p.progress + job, y);
+            else { tma_wait_all<8>(); st_release(p.progress + job, y - 7); }
+        }
         if (++slot == IST) { slot = 0; par ^= 1; }
         if (++ob == 3) ob = 0;
         if (++rf == NFG) rf = 0;
@@ -402,6 +411,8 @@ __global__ void __launch_bounds__(256) k_opt_iir_w(const IirWParams p)
         hs ^= 1;
     }
     if (!ASYNC && lane == 0) tma_wait_all<0>();
+    __syncwarp();
+    if (p.progress && lane == 0) st_release(p.progress + job, H);
 }
 
 
@@ -488,17 +499,19 @@ __global__ void __launch_bounds__(32 * (2 * TPC + 1), TPC == 2 ? 5 : 1) k_opt_ii
     }
     fence_proxy_async();                                     // the zero fill precedes the bulk copies into the same smem
     __syncthreads();                                         // tickets + barrier init visible to every warp; last CTA-wide barrier
+    pdl_launch_dependents();
 
     if (is_prod) {
         // =========================================== producer: one thread feeds the CTA's strips ===========================================
         if (lane != 0) return;
         const uint8_t *gi[TPC], *gr[TPC];
         uint32_t nb_rgb[TPC], nb_rec[TPC];
-        int yy[TPC], sl[TPC], pr[TPC];
+        int yy[TPC], sl[TPC], pr[TPC], jbs[TPC];
 #pragma unroll
         for (int t = 0; t < TPC; t++) {
             const int jb = *reinterpret_cast<volatile int *>(smem + MTAB_BYTES + (size_t)t * SM::bytes + SM::off_job);
             const bool valid = jb < p.N * p.S;
+            jbs[t] = jb;
             const int pg = valid ? jb / p.S : 0, stp = valid ? jb - pg * p.S : 0;
             const int oc = min(p.W - stp * SWW, SWW);
             nb_rgb[t] = (uint32_t)((oc * C + 15) & ~15); nb_rec[t] = (uint32_t)((oc * 8 + 15) & ~15);
@@ -520,6 +533,10 @@ __global__ void __launch_bounds__(32 * (2 * TPC + 1), TPC == 2 ? 5 : 1) k_opt_ii
                         tma_load(wt + SM::off_rgb + sl[t] * SM::RGBS, gi[t], nb_rgb[t], fl);
                         tma_load(wt + SM::off_rec + sl[t] * (SWW * 8), gr[t], nb_rec[t], fl);
                         gi[t] += p.ipitch; gr[t] += p.rpitch;
+                        // The bg warp arrived on this stage's empty barrier (release.cta) after the warp barrier of row
+                        // yy - NST, i.e. after every lane's stores of the bg rows before it; the test above (acquire.cta)
+                        // observed that, so this thread's gpu-scope release publishes those rows -- off the sweep's row path.
+                        if (p.progress && yy[t] >= NST && (yy[t] & 31) == 0) st_release(p.progress + jbs[t], yy[t] - NST);
                         yy[t]++;
                         if (++sl[t] == NST) { sl[t] = 0; pr[t] ^= 1; }
                         prog = true;
@@ -796,6 +813,8 @@ __global__ void __launch_bounds__(32 * (2 * TPC + 1), TPC == 2 ? 5 : 1) k_opt_ii
             if (++rbg == NBG) rbg = 0;
             hs ^= 1;
         }
+        __syncwarp();
+        if (p.progress && lane == 0) st_release(p.progress + job, H);
     }
 }
 
@@ -818,7 +837,7 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
                         const uint8_t *rec, int64_t rpitch, int64_t rstride,
                         uint8_t *ofg, int64_t fpitch, int64_t fstride,
                         uint8_t *obg, int64_t bpitch, int64_t bstride,
-                        int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, cudaStream_t st)
+                        int W, int H, int N, uint32_t *mailbox, unsigned *ticket, int wpc, int *progress, cudaStream_t st)
 {
     if (wpc < 1 || wpc > 8) return B200MRC_ERR_UNSUPPORTED;
     const unsigned epoch = g_epoch.fetch_add(1u) % 255u + 1u;    // 1..255
@@ -829,11 +848,12 @@ int launch_opt_iir_warp(const uint8_t *img, int64_t ipitch, int64_t istride, int
     p.img = img; p.ipitch = ipitch; p.istride = istride; p.rec = rec; p.rpitch = rpitch; p.rstride = rstride;
     p.ofg = ofg; p.fpitch = fpitch; p.fstride = fstride; p.obg = obg; p.bpitch = bpitch; p.bstride = bstride;
     p.W = W; p.H = H; p.N = N; p.S = cdiv(W, SWW);
-    p.mailbox = mailbox; p.ticket = ticket;
+    p.mailbox = mailbox; p.ticket = ticket; p.progress = progress;
     p.tag = ((epoch & 0xfu) << 12) | ((epoch >> 4) << 28);
     p.psleep = env.psleep;
     const int jobs = N * p.S;
     B200MRC_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * 4, st));
+    if (progress) B200MRC_CUDA_TRY(cudaMemsetAsync(progress, 0, sizeof(int) * (size_t)jobs, st));
     // Which form (measured on B200, 3300x2550 RGB pages, ms per launch; profiles/r1q_ab_sweep.txt):
     //   pages        4      16     32     64
     //   one warp     2.39   2.44   2.97   3.59      (45 % of the issue slots at 64 pages)

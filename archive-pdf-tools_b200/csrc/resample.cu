@@ -12,6 +12,7 @@
 // The size logic and the coefficient tables are computed on the host once per plan (they depend
 // only on the shapes); the kernels are pure gather-multiply-accumulate byte kernels.
 #include "common.cuh"
+#include "tma.cuh"
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -181,21 +182,45 @@ struct TileParams {
     const int *bounds_h, *kk_h, *bounds_v, *kk_v;
     int offx, offy, ux0, ux1, uy0, uy1;
     int kh[16], kv[16];
+    // FOLLOW form: the input is still being written by the kernel this one was launched behind (programmatic dependent
+    // launch); prog[page * prog_s + x / prog_w] = rows of column strip x / prog_w that are globally visible
+    const int *prog; int prog_s, prog_w, ntx, npages;
 };
 
-template <int C, int F, int T, int TOH>
+// FOLLOW: a 1-D grid ordered (tile row, page, tile column) -- the order in which a row-sequential producer of all pages
+// finishes the input -- whose CTAs wait for their input rows on the producer's progress counters.
+template <int C, int F, int T, int TOH, bool FOLLOW>
 __global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
 {
     constexpr int RMAX = F * TOH + T, HROW = TOW * C;
     __shared__ __align__(16) uint8_t hbuf[RMAX * HROW];
     const int tid = threadIdx.x;
-    const int ox0 = blockIdx.x * TOW, oy0 = blockIdx.y * TOH, page = blockIdx.z;
+    int bx = blockIdx.x, by = blockIdx.y, page = blockIdx.z;
+    if (FOLLOW) {
+        const int per_row = p.ntx * p.npages;
+        by = bx / per_row;
+        const int r = bx - by * per_row;
+        page = r / p.ntx;
+        bx = r - page * p.ntx;
+    }
+    const int ox0 = bx * TOW, oy0 = by * TOH;
     const int ow = min(TOW, p.out_w - ox0), oh = min(TOH, p.out_h - oy0);
     const int ylast = oy0 + oh - 1;
     const int ry0 = p.bounds_v[2 * oy0], rows_in = p.bounds_v[2 * ylast] + p.bounds_v[2 * ylast + 1] - ry0;
     const bool ux = ox0 >= p.ux0 && ox0 + ow <= p.ux1, uy = oy0 >= p.uy0 && oy0 + oh <= p.uy1;
     const uint8_t *in = p.in + (int64_t)page * p.in_stride + (int64_t)ry0 * p.in_pitch;
     uint8_t *out = p.out + (int64_t)page * p.out_stride + (int64_t)oy0 * p.out_pitch + (int64_t)ox0 * C;
+    if (FOLLOW) {
+        if (tid == 0) {
+            const int xl = ox0 + ow - 1, c0 = p.bounds_h[2 * ox0], c1 = p.bounds_h[2 * xl] + p.bounds_h[2 * xl + 1] - 1;
+            const int need = ry0 + rows_in;
+            for (int s = c0 / p.prog_w; s <= c1 / p.prog_w; s++) {
+                const int *q = p.prog + (int64_t)page * p.prog_s + s;
+                while (ld_acquire(q) < need) __nanosleep(400);
+            }
+        }
+        __syncthreads();                                      // thread 0's acquire orders every thread's reads of the input rows
+    }
 
     auto generic_h = [&](int r, int oxl) {                    // one output pixel of input row ry0 + r
         const int ox = ox0 + oxl, xmin = p.bounds_h[2 * ox], cnt = p.bounds_h[2 * ox + 1];
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(256) k_resample_tile(const TileParams p)
             const uint32_t *src = reinterpret_cast<const uint32_t *>(in + (int64_t)r * p.in_pitch + (int64_t)(F * (ox0 + 4 * g) + p.offx) * C);
             uint32_t w[NW];
 #pragma unroll
-            for (int i = 0; i < NW; i++) w[i] = __ldg(src + i);
+            for (int i = 0; i < NW; i++) w[i] = FOLLOW ? src[i] : __ldg(src + i);   // FOLLOW: written during this kernel's lifetime, no non-coherent loads
             int acc[4][C];
 #pragma unroll
             for (int px = 0; px < 4; px++)
@@ -353,6 +378,72 @@ int upload(const std::vector<int> &v, int **d)
 }
 
 }  // namespace
+}  // namespace b200mrc
+
+namespace b200mrc {
+
+static bool tile_form_ok(const b200mrc_resample_plan *pl, const uint8_t *src, int64_t src_pitch, int64_t src_stride,
+                         const uint8_t *out, int64_t out_pitch, int64_t out_page_stride)
+{
+    return pl->tile_F == 3 && pl->tile_T == 12 && !(src_pitch & 3) && !(src_stride & 3) && !((uintptr_t)src & 3) &&
+           !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, 16) <= 65535 && !tune(T_RESAMPLE_2PASS);
+}
+
+template <int C, bool FOLLOW>
+static const void *tile_kernel(int toh)
+{
+    return toh == 64 ? (const void *)k_resample_tile<C, 3, 12, 64, FOLLOW>
+         : toh == 16 ? (const void *)k_resample_tile<C, 3, 12, 16, FOLLOW> : (const void *)k_resample_tile<C, 3, 12, 32, FOLLOW>;
+}
+
+// prog != null: the FOLLOW form, launched as the programmatic dependent of the kernel before it in `st`
+static int launch_tile(const b200mrc_resample_plan *pl, const uint8_t *src, int64_t src_pitch, int64_t src_stride,
+                       uint8_t *out, int64_t out_pitch, int64_t out_page_stride, int n_pages,
+                       const int *prog, int prog_s, int prog_w, cudaStream_t st)
+{
+    TileParams t;
+    t.in = src; t.in_pitch = src_pitch; t.in_stride = src_stride; t.out = out; t.out_pitch = out_pitch; t.out_stride = out_page_stride;
+    t.in_w = pl->SW; t.in_h = pl->SH; t.out_w = pl->OW; t.out_h = pl->OH; t.ksize_h = pl->ksize_h; t.ksize_v = pl->ksize_v;
+    t.bounds_h = pl->d_bounds_h; t.kk_h = pl->d_kk_h; t.bounds_v = pl->d_bounds_v; t.kk_v = pl->d_kk_v;
+    t.offx = pl->offx; t.offy = pl->offy; t.ux0 = pl->ux0; t.ux1 = pl->ux1; t.uy0 = pl->uy0; t.uy1 = pl->uy1;
+    memcpy(t.kh, pl->kh, sizeof(t.kh)); memcpy(t.kv, pl->kv, sizeof(t.kv));
+    int toh = tune(T_TILE_H);
+    toh = toh == 64 ? 64 : (toh == 16 ? 16 : 32);
+    const int ntx = cdiv(pl->OW, TOW), nty = cdiv(pl->OH, toh);
+    t.prog = prog; t.prog_s = prog_s; t.prog_w = prog_w; t.ntx = ntx; t.npages = n_pages;
+    void *args[] = {(void *)&t};
+    ProfScope _ps("k_resample_tile", st);
+    if (!prog) {
+        const void *kern = pl->C == 1 ? tile_kernel<1, false>(toh) : tile_kernel<3, false>(toh);
+        B200MRC_CUDA_TRY(cudaLaunchKernel(kern, dim3(ntx, nty, n_pages), dim3(256), args, 0, st));
+    } else {
+        if ((int64_t)ntx * nty * n_pages > 0x7fffffffll) return B200MRC_ERR_UNSUPPORTED;
+        const void *kern = pl->C == 1 ? tile_kernel<1, true>(toh) : tile_kernel<3, true>(toh);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ntx * nty * n_pages)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        B200MRC_CUDA_TRY(cudaLaunchKernelExC(&cfg, kern, args));
+    }
+    count_launch();
+    return B200MRC_OK;
+}
+
+// The thumbnail of images a row-sequential kernel is still writing: that kernel (the one launched right before this call
+// in `stream`) publishes per page and per strip of prog_w columns the rows that are complete, and lets its dependents
+// start early (pdl_launch_dependents).  UNSUPPORTED when the plan does not take the tile form (call b200mrc_resample).
+int launch_resample_follow(const b200mrc_resample_plan *pl, const uint8_t *in, int64_t in_pitch, int64_t in_page_stride,
+                           uint8_t *out, int64_t out_pitch, int64_t out_page_stride, int n_pages,
+                           const int *prog, int prog_s, int prog_w, cudaStream_t st)
+{
+    if (!pl || !in || !out || !prog || n_pages <= 0 || prog_w <= 0) return B200MRC_ERR_INVALID;
+    if (pl->fx > 1 || pl->fy > 1 || !pl->need_h || !pl->need_v) return B200MRC_ERR_UNSUPPORTED;
+    if (!tile_form_ok(pl, in, in_pitch, in_page_stride, out, out_pitch, out_page_stride)) return B200MRC_ERR_UNSUPPORTED;
+    return launch_tile(pl, in, in_pitch, in_page_stride, out, out_pitch, out_page_stride, n_pages, prog, prog_s, prog_w, st);
+}
+
 }  // namespace b200mrc
 
 using namespace b200mrc;
@@ -489,29 +580,8 @@ extern "C" int b200mrc_resample(const b200mrc_resample_plan *pl,
                                                (size_t)pl->OW * pl->C, (size_t)pl->OH, cudaMemcpyDeviceToDevice, st));
         return B200MRC_OK;
     }
-    if (pl->tile_F == 3 && pl->tile_T == 12 && !(src_pitch & 3) && !(src_stride & 3) && !((uintptr_t)src & 3) &&
-        !(out_pitch & 3) && !(out_page_stride & 3) && !((uintptr_t)out & 3) && cdiv(pl->OH, 16) <= 65535 && !tune(T_RESAMPLE_2PASS)) {
-        TileParams t;
-        t.in = src; t.in_pitch = src_pitch; t.in_stride = src_stride; t.out = out; t.out_pitch = out_pitch; t.out_stride = out_page_stride;
-        t.in_w = pl->SW; t.in_h = pl->SH; t.out_w = pl->OW; t.out_h = pl->OH; t.ksize_h = pl->ksize_h; t.ksize_v = pl->ksize_v;
-        t.bounds_h = pl->d_bounds_h; t.kk_h = pl->d_kk_h; t.bounds_v = pl->d_bounds_v; t.kk_v = pl->d_kk_v;
-        t.offx = pl->offx; t.offy = pl->offy; t.ux0 = pl->ux0; t.ux1 = pl->ux1; t.uy0 = pl->uy0; t.uy1 = pl->uy1;
-        memcpy(t.kh, pl->kh, sizeof(t.kh)); memcpy(t.kv, pl->kv, sizeof(t.kv));
-        const int toh = tune(T_TILE_H);
-        dim3 grid(cdiv(pl->OW, TOW), cdiv(pl->OH, toh == 64 ? 64 : (toh == 16 ? 16 : 32)), n_pages);
-        { ProfScope _ps("k_resample_tile", st);
-          if (pl->C == 1) {
-              if (toh == 64) k_resample_tile<1, 3, 12, 64><<<grid, 256, 0, st>>>(t);
-              else if (toh == 16) k_resample_tile<1, 3, 12, 16><<<grid, 256, 0, st>>>(t);
-              else k_resample_tile<1, 3, 12, 32><<<grid, 256, 0, st>>>(t);
-          } else {
-              if (toh == 64) k_resample_tile<3, 3, 12, 64><<<grid, 256, 0, st>>>(t);
-              else if (toh == 16) k_resample_tile<3, 3, 12, 16><<<grid, 256, 0, st>>>(t);
-              else k_resample_tile<3, 3, 12, 32><<<grid, 256, 0, st>>>(t);
-          } }
-        B200MRC_LAUNCH_CHECK();
-        return B200MRC_OK;
-    }
+    if (tile_form_ok(pl, src, src_pitch, src_stride, out, out_pitch, out_page_stride))
+        return launch_tile(pl, src, src_pitch, src_stride, out, out_pitch, out_page_stride, n_pages, nullptr, 0, 0, st);
     if (pl->need_h) {
         ResampleParams h;
         h.in = src; h.in_pitch = src_pitch; h.in_stride = src_stride;

@@ -47,6 +47,10 @@ template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// programmatic dependent launch: the next kernel of the stream, if launched with programmatic stream serialization,
+// may start once every CTA of this grid has executed this (or exited); it must order its reads itself
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire(const int *p)
 {

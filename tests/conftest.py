@@ -85,3 +85,17 @@ def load_golden(name, synth):
              t01=np.unpackbits(z['t01'])[: H * W].reshape(H, W).astype(bool),
              timing_keys=[str(k) for k in z['timing_keys']])
     return g
+
+
+@pytest.fixture
+def tuning():
+    """set(name, value) changes a b200mrc tuning knob (b200mrc_set_tuning) for the test and restores it afterwards."""
+    from archive_pdf_tools_b200 import _lib
+    saved = {}
+
+    def set_(name, value):
+        saved.setdefault(name, _lib.get_tuning(name))
+        _lib.set_tuning(name, value)
+    yield set_
+    for k, v in saved.items():
+        _lib.set_tuning(k, v)

@@ -6,20 +6,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def tuning():
-    """set(name, value) changes a b200mrc tuning knob (b200mrc_set_tuning) for the test and restores it afterwards."""
-    from archive_pdf_tools_b200 import _lib
-    saved = {}
-
-    def set_(name, value):
-        saved.setdefault(name, _lib.get_tuning(name))
-        _lib.set_tuning(name, value)
-    yield set_
-    for k, v in saved.items():
-        _lib.set_tuning(k, v)
-
-
 def _plane(eng, arr, c=None):
     from archive_pdf_tools_b200 import Plane
     a = np.ascontiguousarray(arr)

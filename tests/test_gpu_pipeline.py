@@ -436,3 +436,29 @@ def test_streamed_decomposer_packed_mask(eng, synth):
     assert np.array_equal(out['mask'].numpy(), np.packbits(ref['mask'], axis=-1))
     assert np.array_equal(out['fg'].numpy().reshape(ref['fg'].shape), ref['fg'])
     assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])
+
+
+@pytest.mark.parametrize('form', ['auto', 'single-tma', 'single-async', 'trio'])
+def test_bg_thumbnail_following_the_sweep(eng, synth, orc, tuning, form):
+    """The bg thumbnail pass runs beside the sweep (programmatic dependent launch) and reads bg rows as the sweep's
+    strips publish them: same bytes as the serialized form and as the oracle, for every form of the sweep."""
+    import archive_pdf_tools_b200 as pkg
+    if form != 'auto':
+        mode, _, feed = form.partition('-')
+        tuning('IIRW_MODE', mode)
+        if feed:
+            tuning('IIRW_FEED', feed)
+    pages = np.stack([synth.make_page(300 + i, 1210, 1000, dpi=300, sigma_n=3.0, halftone=(i == 2)) for i in range(5)])
+    tuning('BG_FOLLOW', 0)
+    ref = pkg.decompose_pages(pages, dpi=300, bg_downsample=3, denoise_mask='fast')
+    tuning('BG_FOLLOW', 1)
+    for _ in range(4):
+        res = pkg.decompose_pages(pages, dpi=300, bg_downsample=3, denoise_mask='fast')
+        assert np.array_equal(res['bg'], ref['bg']) and np.array_equal(res['fg'], ref['fg'])
+    exp = orc.decompose(pages[2], dpi=300, bg_downsample=3, denoise_mask='fast')
+    assert np.array_equal(res['bg'][2], exp['bg'])
+    # fg and bg both thumbnailed: the follower still takes the bg, the fg pass runs behind it
+    res2 = pkg.decompose_pages(pages[:2], dpi=300, bg_downsample=3, fg_downsample=2, denoise_mask='fast')
+    tuning('BG_FOLLOW', 0)
+    ref2 = pkg.decompose_pages(pages[:2], dpi=300, bg_downsample=3, fg_downsample=2, denoise_mask='fast')
+    assert np.array_equal(res2['bg'], ref2['bg']) and np.array_equal(res2['fg'], ref2['fg'])
