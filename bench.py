@@ -566,7 +566,7 @@ def main():
                 'traffic': traffic.get('step_total'), 'peak_source': peak_src,
                 'algorithmic_bytes_per_px': cfg['bytes_px'],
                 'note': 'achieved = algorithmic bytes of the whole path (inputs once + reference-visible outputs once) / ms_per_step; '
-                        'per_kernel: ms per step from a serialised pass of the same step (one page group, one stream), alg_bytes = the '
+                        'per_kernel: ms per step from a serialised pass of the same step (event-bracketed launches: the bg thumbnail pass, which in the timed step runs beside the sweep as its programmatic dependent, is serialised behind it here, so the rows add up to more than ms_per_step), alg_bytes = the '
                         'kernel\'s own compulsory bytes (DESIGN.md section 3), dram_bytes = ncu dram__bytes per step (profiles/traffic.json)',
                 'dominant': dict(per_kernel.get(dom, {}), kernel=dom) if dom else None,
                 'per_kernel': per_kernel, 'ms_per_step_serialized': serial_ms}

@@ -462,3 +462,20 @@ def test_bg_thumbnail_following_the_sweep(eng, synth, orc, tuning, form):
     tuning('BG_FOLLOW', 0)
     ref2 = pkg.decompose_pages(pages[:2], dpi=300, bg_downsample=3, fg_downsample=2, denoise_mask='fast')
     assert np.array_equal(res2['bg'], ref2['bg']) and np.array_equal(res2['fg'], ref2['fg'])
+
+
+def test_bg_follower_with_more_strips_than_fit_on_the_gpu(eng, synth, orc, tuning):
+    """700 small pages x 3 strips: the sweep's CTAs do not all fit on the GPU at once, so its dependents start late
+    (after the last sweep CTA has started) -- results must not change, and nothing may dead-lock."""
+    import archive_pdf_tools_b200 as pkg
+    distinct = [synth.make_page(400 + i, 120, 300, dpi=100, sigma_n=3.0) for i in range(7)]
+    pages = np.stack([distinct[i % 7] for i in range(700)])
+    tuning('IIRW_MODE', 'single')
+    res = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
+    tuning('BG_FOLLOW', 0)
+    ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
+    assert res['bg'].shape == (700, 40, 100, 3)
+    assert np.array_equal(res['bg'], ref['bg']) and np.array_equal(res['fg'], ref['fg']) and np.array_equal(res['mask'], ref['mask'])
+    for i in (0, 3, 699):
+        exp = orc.decompose(pages[i], dpi=100, bg_downsample=3, denoise_mask='fast')
+        assert np.array_equal(res['bg'][i], exp['bg']) and np.array_equal(res['fg'][i], exp['fg'])
