@@ -83,6 +83,7 @@ PROTOTYPES = {
     'b200mrc_rects_count_nonzero': (C.c_int, [vp, C.c_int, vp, vp]),
     'b200mrc_rects_sigma_bool': (C.c_int, [vp, C.c_int, vp, vp]),
     'b200mrc_pack_mask': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    'b200mrc_host_unpack_mask': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int]),
     'b200mrc_channel_stats': (C.c_int, [vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]),
     'b200mrc_special_gray': (C.c_int, [vp, i64, i64, vp, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     'b200mrc_decompose_workspace_bytes': (C.c_size_t, [C.POINTER(DecomposeArgs)]),

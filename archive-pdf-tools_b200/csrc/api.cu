@@ -273,8 +273,11 @@ int decompose_group(const b200mrc_decompose_args *a, const DecomposeLayout &L, i
     uint8_t *bg_full = a->bg_plan ? ws + L.off_bgfull + (size_t)p0 * L.full_page : bg_out;
     const int64_t fgp = a->fg_plan ? (int64_t)L.full_pitch : a->fg_pitch, fgs = a->fg_plan ? (int64_t)L.full_page : a->fg_page_stride;
     const int64_t bgp = a->bg_plan ? (int64_t)L.full_pitch : a->bg_pitch, bgs = a->bg_plan ? (int64_t)L.full_page : a->bg_page_stride;
-    // tuning key BG_FOLLOW (default on): the bg thumbnail runs as a follower of the sweep
-    const bool follow = a->bg_plan && tune(T_BG_FOLLOW) != 0;
+    // tuning key BG_FOLLOW: the bg thumbnail runs as a follower of the sweep.  1 (default): only when the sweep fills the GPU
+    // (>= 6 strips per SM) -- below that its waiting CTAs would take the SM slots that kernels of other streams (the
+    // next chunk of a streamed batch) could use, which is worth more than the follower; 2: always; 0: never
+    const int follow_mode = tune(T_BG_FOLLOW);
+    const bool follow = a->bg_plan && (follow_mode >= 2 || (follow_mode == 1 && (int64_t)n * cdiv(W, 128) >= 6 * (int64_t)dev_info().sm_count));
     int *bg_prog = nullptr;
     bool bg_done = false;
     rc = launch_optimise(mask, a->mask_pitch, a->mask_page_stride, img, a->img_pitch, a->img_page_stride, C,

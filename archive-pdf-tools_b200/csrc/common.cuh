@@ -60,7 +60,7 @@ enum TuneKey {
     T_TILE_H,           // tile resampler: output rows per CTA (16 | 32 | 64)
     T_DECOMPOSE_GROUPS, // page groups per b200mrc_decompose call (0 auto)
     T_DECOMPOSE_STREAMS,// internal streams the groups run on (0 auto)
-    T_BG_FOLLOW,        // 1: the bg thumbnail pass follows the sweep's progress counters (programmatic dependent launch); 0: runs after it
+    T_BG_FOLLOW,        // the bg thumbnail pass follows the sweep's progress counters (programmatic dependent launch): 1 when the sweep fills the GPU, 2 always, 0 never (runs after it)
     T_COUNT
 };
 int tune(TuneKey k);

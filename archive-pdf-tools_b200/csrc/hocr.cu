@@ -10,6 +10,8 @@
 // restatement it is tested against is oracle/mrc_oracle.c orc_estimate_sigma_bool.
 // The Sauvola passes on the crops (k = 0.1, plain and inverted input) are b200mrc_sauvola calls.
 #include "common.cuh"
+#include <cstring>
+#include <mutex>
 #include <math_constants.h>
 
 namespace b200mrc {
@@ -192,6 +194,38 @@ extern "C" int b200mrc_pack_mask(const uint8_t *mask, int64_t pitch, int64_t pag
     { ProfScope _ps("k_pack_mask", (cudaStream_t)stream);
       k_pack_mask<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, pitch, page_stride, packed, packed_pitch, packed_page_stride, width, height, invert ? 1 : 0); }
     B200MRC_LAUNCH_CHECK();
+    return B200MRC_OK;
+}
+
+// Host side of the packed hand-off: mode-'1' rows that crossed the bus (1 bit per pixel) back into the bool plane the
+// reference's callers index (mrc.py:399 yields a bool H x W array).  Plain C++ on HOST memory, one thread per call
+// (callers run it from worker threads, one call per chunk of pages); no CUDA call inside.
+extern "C" int b200mrc_host_unpack_mask(const uint8_t *packed, int64_t packed_pitch, int64_t packed_page_stride,
+                                        uint8_t *mask, int64_t pitch, int64_t page_stride,
+                                        int width, int height, int n_pages)
+{
+    if (!packed || !mask || width <= 0 || height <= 0 || n_pages <= 0) return B200MRC_ERR_INVALID;
+    if (packed_pitch < (width + 7) / 8 || pitch < width) return B200MRC_ERR_INVALID;
+    static uint64_t lut[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int b = 0; b < 256; b++) {
+            uint64_t v = 0;
+            for (int i = 0; i < 8; i++) v |= (uint64_t)((b >> (7 - i)) & 1) << (8 * i);      // first pixel = most significant bit
+            lut[b] = v;
+        }
+    });
+    const int full = width / 8, rest = width - 8 * full;
+    for (int n = 0; n < n_pages; n++)
+        for (int y = 0; y < height; y++) {
+            const uint8_t *src = packed + (int64_t)n * packed_page_stride + (int64_t)y * packed_pitch;
+            uint8_t *dst = mask + (int64_t)n * page_stride + (int64_t)y * pitch;
+            for (int i = 0; i < full; i++) memcpy(dst + 8 * i, &lut[src[i]], 8);
+            if (rest) {
+                const uint64_t v = lut[src[full]];
+                memcpy(dst + 8 * full, &v, (size_t)rest);
+            }
+        }
     return B200MRC_OK;
 }
 

@@ -368,6 +368,21 @@ def _copy2d(dst_ptr, dst_pitch, src_ptr, src_pitch, row_bytes, rows, kind, strea
                                    C.c_void_p(stream.cuda_stream)), 'b200mrc_copy2d')
 
 
+class _PendingBatch:
+    """What StreamedDecomposer.run_async returns when host workers finish the batch: synchronize() like a CUDA event."""
+
+    def __init__(self, event, futures):
+        self.event, self.futures = event, futures
+
+    def synchronize(self):
+        self.event.synchronize()
+        for f in self.futures:
+            f.result()                                             # re-raises a worker's exception
+
+    def query(self):
+        return self.event.query() and all(f.done() for f in self.futures)
+
+
 class StreamedDecomposer:
     """Host-to-host decomposition of a large batch in chunks.  H2D of later chunks, the kernels of up to
     `compute_streams` chunks and D2H of finished chunks run concurrently (copy engines + SMs) over a ring of
@@ -376,8 +391,20 @@ class StreamedDecomposer:
     pinned."""
 
     def __init__(self, eng, n_pages, h, w, c, chunk=4, bg_downsample=None, fg_downsample=None, mask_only=False,
-                 buffers=4, compute_streams=2, packed_mask=False):
+                 buffers=4, compute_streams=2, packed_mask=False, mask_transport='packed', unpack_workers=3):
         self.eng, self.n, self.h, self.w, self.c = eng, n_pages, h, w, c
+        # mask_transport='packed' (default): the mask crosses the bus as mode-'1' rows (1 bit per pixel) and worker
+        # threads expand it on the host into the bool plane the reference yields (b200mrc_host_unpack_mask) -- same
+        # result arrays as 'bool' (the 1-byte plane itself over the bus), 20 % fewer D2H bytes per RGB page: 12.9
+        # against 10.8 Gpx/s host to host on one B200, 3 workers at 4.5 GB/s each keep up (profiles/r2r_e2e_sweep.txt).
+        # packed_mask=True hands the packed rows themselves to the caller.
+        assert mask_transport in ('bool', 'packed')
+        self.host_unpack = mask_transport == 'packed' and not packed_mask
+        self.pool = None
+        if self.host_unpack:
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(max_workers=max(1, unpack_workers), thread_name_prefix='b200mrc-unpack')
+            packed_mask = True                                     # device side and D2H: exactly the packed hand-off
         self.chunk = max(1, min(chunk, n_pages))
         n_chunks = (n_pages + self.chunk - 1) // self.chunk
         self.nb = max(1, min(buffers, n_chunks))
@@ -404,10 +431,26 @@ class StreamedDecomposer:
         self.st_out = [dict(mask=mask_stage(b_.mask), fg=None if mask_only else stage(b_.fg), bg=None if mask_only else stage(b_.bg))
                        for b_ in self.batches]
 
+    def close(self):
+        """Stop the host unpack workers (idempotent)."""
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def alloc_outputs(self):
         """Pinned host result buffers: mask [N,H,W] u8 (0/1) -- or [N,H,ceil(W/8)] packed rows with packed_mask --,
         fg [N,fh,fw*C], bg [N,bh,bw*C]."""
         o = {'mask': torch.empty((self.n,) + self.out_shapes['mask'], dtype=torch.uint8).pin_memory()}
+        if self.host_unpack:
+            # the D2H target stays the pinned packed plane; 'mask' is the bool plane the workers fill (CPU writes: pageable)
+            o['mask_packed'] = o['mask']
+            o['mask'] = torch.empty((self.n, self.h, self.w), dtype=torch.uint8)
         if not self.mask_only:
             o['fg'] = torch.empty((self.n,) + self.out_shapes['fg'], dtype=torch.uint8).pin_memory()
             o['bg'] = torch.empty((self.n,) + self.out_shapes['bg'], dtype=torch.uint8).pin_memory()
@@ -434,6 +477,7 @@ class StreamedDecomposer:
         # last users of every device buffer slot, carried over from the previous call
         tail_cmp, tail_out = getattr(self, '_tail_cmp', {}), getattr(self, '_tail_out', {})
         in_done, cmp_done, out_done = {}, {}, {}
+        futures = []
         n_chunks = (n + ck - 1) // ck
         names = ('mask',) if self.mask_only else ('mask', 'fg', 'bg')
         for i in range(n_chunks):
@@ -473,8 +517,19 @@ class StreamedDecomposer:
                 self.s_out.wait_event(cmp_done[i])
                 for name in names:
                     plane, st = getattr(b, name), self.st_out[slot][name]
-                    out[name][lo:hi].copy_((st if st is not None else plane.t)[:m], non_blocking=True)
+                    dst = out['mask_packed'] if (name == 'mask' and self.host_unpack) else out[name]
+                    dst[lo:hi].copy_((st if st is not None else plane.t)[:m], non_blocking=True)
+                    if name == 'mask' and self.host_unpack:
+                        futures.append(self.pool.submit(self._unpack, self.s_out.record_event(), out, lo, hi))
                 out_done[i] = self.s_out.record_event()
             tail_cmp[slot], tail_out[slot] = cmp_done[i], out_done[i]
         self._tail_cmp, self._tail_out = tail_cmp, tail_out
-        return out_done[n_chunks - 1]
+        return _PendingBatch(out_done[n_chunks - 1], futures) if self.host_unpack else out_done[n_chunks - 1]
+
+    def _unpack(self, ev, out, lo, hi):
+        """Worker thread: wait for the chunk's packed rows to land, expand them into out['mask'][lo:hi] (both calls release the GIL)."""
+        ev.synchronize()
+        pk, mk = out['mask_packed'], out['mask']
+        rb = pk.shape[2]
+        L.check(L.lib().b200mrc_host_unpack_mask(C.c_void_p(pk[lo].data_ptr()), rb, self.h * rb, C.c_void_p(mk[lo].data_ptr()), self.w,
+                                                 self.h * self.w, self.w, self.h, hi - lo), 'b200mrc_host_unpack_mask')

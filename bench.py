@@ -438,9 +438,10 @@ def main():
         e2e_buffers = int(os.environ.get('B200MRC_E2E_BUFFERS', '4'))
         last = 'mask' if cfg['mask_only'] else 'bg'
 
-        def measure_e2e(packed):
+        def measure_e2e(packed, transport='packed'):
             sd = StreamedDecomposer(run.eng, N, H, W, C, chunk=e2e_chunk, bg_downsample=cfg['bg'], buffers=e2e_buffers,
-                                    compute_streams=e2e_streams, mask_only=cfg['mask_only'], packed_mask=packed)
+                                    compute_streams=e2e_streams, mask_only=cfg['mask_only'], packed_mask=packed,
+                                    mask_transport=transport)
             # a book is a stream of batches: two batches in flight (each with its own pinned result buffers), so the H2D
             # copies and kernels of step i+1 overlap the D2H tail of step i; every step's inputs cross PCIe and every
             # step's results are waited for and read on the host inside the timed region
@@ -479,13 +480,15 @@ def main():
             # once, all ranks concurrently, no kernels (what the host<->device path of this box can deliver at N GPUs)
             s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
             dev_in = torch.empty_like(host, device='cuda')
-            dev_out = {k: torch.empty_like(v, device='cuda') for k, v in outs2[0].items()}
+            # what crosses the bus: with the packed transport the bool plane 'mask' is filled by host workers from 'mask_packed'
+            wire = {k: v for k, v in outs2[0].items() if not (k == 'mask' and 'mask_packed' in outs2[0])}
+            dev_out = {k: torch.empty_like(v, device='cuda') for k, v in wire.items()}
 
             def copy_only():
                 with torch.cuda.stream(s_h2d):
                     dev_in.copy_(host, non_blocking=True)
                 with torch.cuda.stream(s_d2h):
-                    for k, v in outs2[0].items():
+                    for k, v in wire.items():
                         v.copy_(dev_out[k], non_blocking=True)
 
             copy_only(); torch.cuda.synchronize(); barrier()
@@ -499,8 +502,10 @@ def main():
                    'ms_per_step': dt / e2e_steps * 1e3, 'copy_only_ms_per_step': dt_copy * 1e3,
                    'frac_of_copy_ceiling': dt_copy / (dt / e2e_steps),
                    'h2d_bytes_per_step': int(host.numel()) * world,
-                   'd2h_bytes_per_step': int(sum(v.numel() for v in outs2[0].values())) * world,
-                   'one_call_at_a_time': px_step * e2e_steps / dt_sync / 1e6, 'batches_in_flight': 2, 'packed_mask': packed}
+                   'd2h_bytes_per_step': int(sum(v.numel() for v in wire.values())) * world,
+                   'one_call_at_a_time': px_step * e2e_steps / dt_sync / 1e6, 'batches_in_flight': 2, 'packed_mask': packed,
+                   'mask_transport': transport}
+            sd.close()
             del sd, outs2, dev_in, dev_out
             torch.cuda.empty_cache()
             return res
@@ -510,9 +515,14 @@ def main():
                                     'host<->device ceiling of this box at this N; frac = copy_only time / e2e step time')
         e2e['api'] = ('archive_pdf_tools_b200.engine.StreamedDecomposer.run_async: pinned host pages -> 1-D H2D DMA -> device pitching '
                       '(b200mrc_copy2d) -> b200mrc_decompose (%d-page chunks, %d compute streams, %d device buffers) -> device '
-                      'unpitching -> 1-D D2H DMA of mask/fg/bg into pinned host buffers' % (e2e_chunk, e2e_streams, e2e_buffers))
+                      'unpitching, mask packed to 1 bit per pixel (b200mrc_pack_mask) -> 1-D D2H DMA of mask/fg/bg into pinned host '
+                      'buffers -> 3 host worker threads expand the mask rows into the bool plane the reference yields '
+                      '(b200mrc_host_unpack_mask); the step is done when the bool plane, fg and bg are in host memory'
+                      % (e2e_chunk, e2e_streams, e2e_buffers))
+        # the same results with the 1-byte bool plane itself crossing the bus (round-1 behaviour; no host workers)
+        e2e['bool_transport_variant'] = measure_e2e(False, 'bool')
         # the same path handing the mask over as PIL mode-'1' rows (b200mrc_pack_mask: what encode_mrc_mask, mrc.py:474-520,
-        # builds from the bool array anyway): 8x fewer mask bytes over PCIe.  Reported separately: `value` above returns the
+        # builds from the bool array anyway): no host unpack at all.  Reported separately: `value` above returns the
         # reference's own bool plane.
         e2e['packed_mask_variant'] = measure_e2e(True)
 

@@ -206,6 +206,14 @@ B200MRC_API int b200mrc_pack_mask(const uint8_t *mask, int64_t pitch, int64_t pa
                       uint8_t *packed, int64_t packed_pitch, int64_t packed_page_stride,
                       int width, int height, int n_pages, int invert, void *stream);
 
+/* ... and back on the HOST: packed rows that crossed the bus -> the bool (0/1 byte) plane the reference's callers index
+ * (the first yield of create_mrc_hocr_components, mrc.py:399; == np.unpackbits(packed, axis=1)[:, :width]).  `packed`
+ * and `mask` are HOST pointers; plain single-threaded C++ (call it from worker threads, one call per chunk of pages);
+ * little-endian hosts. */
+B200MRC_API int b200mrc_host_unpack_mask(const uint8_t *packed, int64_t packed_pitch, int64_t packed_page_stride,
+                             uint8_t *mask, int64_t pitch, int64_t page_stride,
+                             int width, int height, int n_pages);
+
 /* A12  special_gray_convert (grayconvert.py:38-66).  Two steps with a host decision between them,
  * exactly like the reference: (1) per-channel min / max / sum / sum-of-squares of each page
  * (`stats_out`: n_pages x 3 x 4 uint64 on the DEVICE: min, max, sum, sumsq), (2) per-pixel level

@@ -73,3 +73,19 @@ def test_synth_pages_are_deterministic(synth):
     assert a.shape == (120, 90, 3) and np.array_equal(a, b)
     g = synth.make_page(3, 120, 90, dpi=100, rgb=False, halftone=True)
     assert g.shape == (120, 90)
+
+
+def test_host_unpack_mask_is_unpackbits():
+    """b200mrc_host_unpack_mask runs on HOST memory (no CUDA call): np.unpackbits of mode-'1' rows, ragged widths,
+    pitched destination left untouched outside the page."""
+    import numpy as np
+    from archive_pdf_tools_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    for n, h, w in [(2, 37, 61), (1, 5, 8), (3, 20, 7), (1, 3, 1), (2, 64, 2550)]:
+        m = rng.random((n, h, w)) < 0.3
+        p = np.packbits(m, axis=2)
+        out = np.full((n, h, w + 3), 7, np.uint8)
+        rc = L.lib().b200mrc_host_unpack_mask(p.ctypes.data, p.shape[2], p.shape[1] * p.shape[2], out.ctypes.data, w + 3, h * (w + 3), w, h, n)
+        assert rc == 0
+        assert np.array_equal(out[:, :, :w], m.view(np.uint8)) and (out[:, :, w:] == 7).all()
+    assert L.lib().b200mrc_host_unpack_mask(None, 1, 1, None, 1, 1, 1, 1, 1) != 0

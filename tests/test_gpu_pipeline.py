@@ -166,7 +166,8 @@ def test_streamed_decomposer_matches_batched(eng, synth):
     pages = np.stack([synth.make_page(300 + i, 270, 330, dpi=100, sigma_n=3.0, halftone=(i == 2)) for i in range(7)])
     ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
     host = torch.from_numpy(pages).pin_memory()
-    for kw in (dict(chunk=2), dict(chunk=2, buffers=2, compute_streams=1), dict(chunk=3, buffers=3, compute_streams=3), dict(chunk=7)):
+    for kw in (dict(chunk=2), dict(chunk=2, buffers=2, compute_streams=1, mask_transport='bool'), dict(chunk=3, buffers=3, compute_streams=3),
+               dict(chunk=7, mask_transport='bool')):
         sd = StreamedDecomposer(eng, 7, 270, 330, 3, bg_downsample=3, **kw)
         out = sd.alloc_outputs()
         for _ in range(2):
@@ -187,7 +188,7 @@ def test_streamed_decomposer_back_to_back_calls(eng, synth):
     sets = [np.stack([synth.make_page(400 + 10 * j + i, 270, 330, dpi=100, sigma_n=3.0, halftone=(i == 1)) for i in range(5)]) for j in range(3)]
     refs = [pkg.decompose_pages(pg, dpi=100, bg_downsample=3, denoise_mask='fast') for pg in sets]
     hosts = [torch.from_numpy(pg).pin_memory() for pg in sets]
-    for kw in (dict(chunk=2), dict(chunk=1, buffers=3, compute_streams=3), dict(chunk=5)):
+    for kw in (dict(chunk=2), dict(chunk=1, buffers=3, compute_streams=3, mask_transport='bool'), dict(chunk=5)):
         sd = StreamedDecomposer(eng, 5, 270, 330, 3, bg_downsample=3, **kw)
         outs = [sd.alloc_outputs() for _ in range(3)]
         for rep in range(2):
@@ -438,6 +439,30 @@ def test_streamed_decomposer_packed_mask(eng, synth):
     assert np.array_equal(out['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])
 
 
+def test_streamed_decomposer_packed_transport_returns_the_bool_plane(eng, synth):
+    """mask_transport='packed': 1 bit per pixel over the bus, worker threads expand it on the host
+    (b200mrc_host_unpack_mask) -- the caller gets the same bool plane, fg and bg as with the default transport."""
+    import torch
+    import archive_pdf_tools_b200 as pkg
+    from archive_pdf_tools_b200.engine import StreamedDecomposer
+    pages = np.stack([synth.make_page(500 + i, 130, 203, dpi=100) for i in range(11)])
+    ref = pkg.decompose_pages(pages, dpi=100, bg_downsample=3, denoise_mask='fast')
+    host = torch.from_numpy(pages).pin_memory()
+    sd = StreamedDecomposer(eng, 11, 130, 203, 3, chunk=2, buffers=2, bg_downsample=3, mask_transport='packed', unpack_workers=3)
+    outs = [sd.alloc_outputs() for _ in range(2)]
+    for o in outs:
+        o['mask'].fill_(9)
+    pend = [sd.run_async(host, o, 25, denoise_mask='fast') for o in outs]            # two calls in flight
+    for p, o in zip(pend, outs):
+        p.synchronize()
+        assert p.query()
+        assert o['mask'].shape == (11, 130, 203)
+        assert np.array_equal(o['mask'].numpy(), ref['mask'].view(np.uint8))
+        assert np.array_equal(o['fg'].numpy().reshape(ref['fg'].shape), ref['fg'])
+        assert np.array_equal(o['bg'].numpy().reshape(ref['bg'].shape), ref['bg'])
+    sd.close()
+
+
 @pytest.mark.parametrize('form', ['auto', 'single-tma', 'single-async', 'trio'])
 def test_bg_thumbnail_following_the_sweep(eng, synth, orc, tuning, form):
     """The bg thumbnail pass runs beside the sweep (programmatic dependent launch) and reads bg rows as the sweep's
@@ -451,7 +476,7 @@ def test_bg_thumbnail_following_the_sweep(eng, synth, orc, tuning, form):
     pages = np.stack([synth.make_page(300 + i, 1210, 1000, dpi=300, sigma_n=3.0, halftone=(i == 2)) for i in range(5)])
     tuning('BG_FOLLOW', 0)
     ref = pkg.decompose_pages(pages, dpi=300, bg_downsample=3, denoise_mask='fast')
-    tuning('BG_FOLLOW', 1)
+    tuning('BG_FOLLOW', 2)                       # 2 = follow at every batch size (1, the default: only when the sweep fills the GPU)
     for _ in range(4):
         res = pkg.decompose_pages(pages, dpi=300, bg_downsample=3, denoise_mask='fast')
         assert np.array_equal(res['bg'], ref['bg']) and np.array_equal(res['fg'], ref['fg'])
