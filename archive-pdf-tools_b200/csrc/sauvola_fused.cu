@@ -23,11 +23,12 @@
 // Pages whose blur radius exceeds 2 (sigma_est >= 22.5) are pre-blurred into the gray plane by gray_blur.cu's tiled
 // kernels and thresholded from there (no production step).  Algorithmic HBM bytes: C in + 1 out per pixel.
 #include "common.cuh"
+#include <map>
+#include <mutex>
 #include "blur.cuh"
 #include "tma.cuh"
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 
 namespace b200mrc {
 
@@ -54,6 +55,7 @@ struct FusedParams {
     int n_strips, strip_w, ext_left, n_bands, band_h;
     int sps, eb;                                                // prefix plane stride (entries per residue row); bias of the entry indices
     double km1, k2;
+    const uint16_t *vmin;               // decision table (below): pixel p with window mean m is foreground iff variance >= vmin[m << 8 | p]
     int flags;
     int out8;                                                   // out rows allow 8-byte stores
     int dbg;                                                    // FUSED_DBG = 1: skip the per-pixel test (timing experiments only; the mask is wrong)
@@ -130,6 +132,7 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
     uint64_t *rowbar = reinterpret_cast<uint64_t *>(smem + L.off_rowbar);
     uint2 *sWT = reinterpret_cast<uint2 *>(smem + L.off_wt);
     const uint2 *sMY = reinterpret_cast<const uint2 *>(smem + L.off_my);
+    const uint16_t *vmin = p.vmin;
     const uint2 *sMX = reinterpret_cast<const uint2 *>(smem + L.off_mx);
     uint8_t *stage = smem + L.off_stage + STAGE_PAD;
     const int stage_stride = (ncols * CS + 2 * STAGE_PAD + 15) & ~15;
@@ -383,14 +386,14 @@ __device__ __forceinline__ void fused_march(const FusedParams &p, uint8_t *smem,
                     const uint2 lo = *reinterpret_cast<const uint2 *>(P + p.bo_lo[k]);
                     S[k] = hi.x - lo.x; Q[k] = hi.y - lo.y;
                 }
+                // The reference's FP64 test is a function of three integers -- pixel, mean m = S / n, variance v = Q / n - m*m --
+                // and monotone in v, so it is tabulated exactly: vmin[m][p] = the least v that makes the pixel foreground
+                // (0: always, 0xffff: never; built once per (k, R) by k_sauvola_vmin with the reference's own operations).
                 auto test_fast = [&](const int k, const uint32_t M, const uint32_t sh) -> uint32_t {
                     const uint32_t m = __umulhi(S[k], M) >> sh, q = __umulhi(Q[k], M) >> sh;
-                    const double md = u2d(m), vd = u2d(q - m * m), pd = u2d(byte_of(cA[k >> 2], k & 3));
-                    const double mm = __dmul_rn(md, md);
-                    const double t = __dadd_rn(pd, __dmul_rn(md, p.km1));
-                    const double rhs = __dmul_rn(__dmul_rn(mm, p.k2), vd);
-                    const double lhs = __dmul_rn(t, t);
-                    return (uint32_t)(t <= 0.0) | (uint32_t)(lhs <= rhs);
+                    const uint32_t v = q - m * m;
+                    const uint32_t T = __ldg(vmin + (((m << 8) | byte_of(cA[k >> 2], k & 3)) & 0xffffu));
+                    return (uint32_t)(v >= T);
                 };
                 uint32_t bits[2] = {0, 0};
                 // (magic, shift) of every pixel's window area: interior columns share the row's entry sMY[ny] (stride 0);
@@ -561,6 +564,52 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sauvola_fused(const FusedParams 
 
 }  // namespace
 
+// vmin[m << 8 | p]: least variance v (integer, 0..65025) for which the reference's test (sauvola.pyx:6-7, k >= 0)
+//   t = p + m*(k - 1);  fg = t <= 0 || t*t <= ((m*m)*k2)*v        (every operation rounded on its own)
+// holds for pixel p and window mean m; 0xffff when no v does.  The right-hand side is monotone in v, so a bisection with
+// the reference's own operations gives the exact boundary: the kernel's integer comparison v >= vmin decides every
+// pixel exactly as the FP64 expression would.
+__global__ void __launch_bounds__(256) k_sauvola_vmin(uint16_t *tab, double km1, double k2)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;              // m << 8 | p
+    const double md = (double)(idx >> 8), pd = (double)(idx & 255);
+    const double t = __dadd_rn(pd, __dmul_rn(md, km1));
+    const double lhs = __dmul_rn(t, t), c = __dmul_rn(__dmul_rn(md, md), k2);
+    auto fg = [&](int v) { return t <= 0.0 || lhs <= __dmul_rn(c, (double)v); };
+    int lo = 0, hi = 65026;                                      // first v in [0, 65026) with fg(v); 65026 = none
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (fg(mid)) hi = mid; else lo = mid + 1;
+    }
+    tab[idx] = lo > 65025 ? (uint16_t)0xffffu : (uint16_t)lo;
+}
+
+// one table per (device, k, R), built at first use on the caller's stream and kept for the life of the process
+struct VminKey { int dev; double k, R; bool operator<(const VminKey &o) const { return dev != o.dev ? dev < o.dev : (k != o.k ? k < o.k : R < o.R); } };
+std::mutex g_vmin_mu;
+std::map<VminKey, uint16_t *> g_vmin;
+
+int sauvola_vmin_table(double k, double Rr, const uint16_t **tab, cudaStream_t st)
+{
+    int dev = 0;
+    B200MRC_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_vmin_mu);
+    auto it = g_vmin.find(VminKey{dev, k, Rr});
+    if (it != g_vmin.end()) { *tab = it->second; return B200MRC_OK; }
+    if (g_vmin.size() >= 64) return B200MRC_ERR_UNSUPPORTED;     // a caller sweeping k: the two-pass kernels take over
+    uint16_t *d = nullptr;
+    B200MRC_CUDA_TRY(cudaMalloc((void **)&d, 65536 * sizeof(uint16_t)));
+    k_sauvola_vmin<<<256, 256, 0, st>>>(d, k - 1.0, k * k / Rr / Rr);
+    count_launch();
+    // later launches may come on other streams: the table must be complete before this call returns (first use only)
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+    g_vmin[VminKey{dev, k, Rr}] = d;
+    *tab = d;
+    return B200MRC_OK;
+}
+
 // Does the fused kernel apply?  16-byte aligned rows (TMA), a window of 3..255, no k < 0 / inverted-input variants.
 bool sauvola_fused_ok(const uint8_t *src, int64_t src_pitch, int64_t src_stride, int C, const uint8_t *out, int64_t out_pitch,
                       int64_t out_stride, int W, int H, int ww, int wh, double k, int flags)
@@ -620,6 +669,7 @@ int launch_sauvola_fused(const uint8_t *src, int64_t src_pitch, int64_t src_stri
         auto bo = [&](int q) { return ((q & 7) * p.sps + (q >> 3)) * 8; };
         p.bo_st[k] = bo(p.eb + k + 1); p.bo_hi[k] = bo(p.eb + p.r + 1 + k); p.bo_lo[k] = bo(p.eb - p.l + 1 + k);
     }
+    { const int trc = sauvola_vmin_table(k, Rr, &p.vmin, st); if (trc != B200MRC_OK) return trc; }
     p.km1 = k - 1.0;
     p.k2 = k * k / Rr / Rr;                                       // sauvola.pyx:60
     p.flags = flags;
