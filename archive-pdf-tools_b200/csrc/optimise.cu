@@ -253,9 +253,12 @@ int plan_optimise(int W, int N, int nfg, int nbg, OptPlan &best)
     // resident warps per SM to hide the row-step latency: the widest such strips (least halo
     // overhead); (2) resident at once: the most warps; (3) a batch too large to be resident runs
     // in ticket order over several waves: 256-column strips (throughput-bound regime).
-    static int cW = -1, cN = -1, cfg = -1, cbg = -1;
-    static OptPlan cplan;
-    if (cW == W && cN == N && cfg == nfg && cbg == nbg) { best = cplan; return B200MRC_OK; }
+    // last plan per host thread (the search calls cudaFuncSetAttribute / the occupancy query ~60 times)
+    thread_local int cW = -1, cN = -1, cfg = -1, cbg = -1, cdev = -1;
+    thread_local OptPlan cplan;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cW == W && cN == N && cfg == nfg && cbg == nbg && cdev == dev) { best = cplan; return B200MRC_OK; }
     OptPlan pick{0, 0, 0, 0}, c;
     double pick_warps = -1.0, warps;
     bool fits, good = false;
@@ -276,7 +279,7 @@ int plan_optimise(int W, int N, int nfg, int nbg, OptPlan &best)
     }
     if (pick.T == 0) return B200MRC_ERR_UNSUPPORTED;
     best = pick;
-    cW = W; cN = N; cfg = nfg; cbg = nbg; cplan = pick;
+    cW = W; cN = N; cfg = nfg; cbg = nbg; cdev = dev; cplan = pick;
     return B200MRC_OK;
 }
 
