@@ -255,6 +255,31 @@ def test_sauvola_both_paths(eng, orc, tuning, path):
                 assert np.array_equal(got[i], orc.sauvola(img[i], ww, ww, k=k)), (path, h, w, ww, i)
 
 
+def test_sauvola_decision_table_over_k_and_R(eng, orc, tuning):
+    """The fused kernel decides through a table vmin[mean][pixel] built per (k, R) (k_sauvola_vmin).  Images that reach the
+    corners of the (pixel, mean, variance) space -- flat black / white, two-level patterns with every contrast, noise of
+    every amplitude -- against the oracle's FP64 test, for k from 0 to beyond 1 and R other than 128."""
+    tuning('THRESHOLD_PATH', 'fused')
+    rng = np.random.default_rng(5)
+    h, w = 96, 1040
+    imgs = []
+    lo = rng.integers(0, 256, (h, 1)).astype(np.int32); hi = rng.integers(0, 256, (1, w)).astype(np.int32)
+    imgs.append(np.where(rng.random((h, w)) < 0.5, lo, hi))                        # two levels of every contrast
+    imgs.append(np.clip(rng.normal(128, np.linspace(0, 90, w)[None, :], (h, w)), 0, 255))   # variance ramp
+    imgs.append(np.tile(np.arange(w) % 256, (h, 1)))                               # every pixel value against slowly moving means
+    imgs.append(np.zeros((h, w))); imgs.append(np.full((h, w), 255))
+    imgs.append(np.where((np.add.outer(np.arange(h), np.arange(w)) // 3) % 2 == 0, 0, 255))
+    img = np.stack(imgs).astype(np.uint8)
+    src = _plane(eng, img); dst = _empty(eng, len(imgs), h, w)
+    for k, R in [(0.34, 128.0), (0.1, 128.0), (0.0, 128.0), (0.05, 128.0), (0.5, 100.0), (0.9, 64.5), (1.0, 128.0), (1.7, 128.0), (0.34, 1.0)]:
+        for ww in (5, 33, 75):
+            eng.sauvola(src, dst, ww, ww, k=k, R=R)
+            got = dst.numpy(np.bool_)
+            for i in range(len(imgs)):
+                exp = orc.sauvola(img[i], ww, ww, k=k, R=R)
+                assert np.array_equal(got[i], exp), (k, R, ww, i, int((got[i] != exp).sum()))
+
+
 def _threshold_expected(orc, page, sig_est, ww, wh, k=0.34):
     gray = page if page.ndim == 2 else orc.rgb2gray(page)
     if sig_est is not None and sig_est > 1.0:
