@@ -14,16 +14,22 @@
 //     epoch in the spare bits of its two 16-bit lanes (sums are < 4096), so a word is either stale
 //     (tag mismatch -> poll again) or complete; jobs are ticketed in dependency order, so any
 //     residency is deadlock-free;
-//   * every warp feeds itself.  Large batches: its lane 0 issues the TMA bulk loads of its input rows (RGB +
-//     8-byte records, IST rows ahead, one mbarrier per stage) and the bulk stores of its staged fg/bg rows.
-//     Small batches (the machine is not full, row latency is everything): lane-private cp.async copies and
-//     re-tiled 16-byte stores, no barrier and no proxy fence (template parameter ASYNC);
+//   * every warp feeds itself: its lane 0 issues the TMA bulk loads of its input rows (RGB + 8-byte records, IST
+//     rows ahead, one mbarrier per stage) and the bulk stores of its staged fg/bg rows.  (Template parameter ASYNC,
+//     tuning key IIRW_FEED=async: lane-private cp.async copies and re-tiled 16-byte stores instead, no barrier and
+//     no proxy fence -- kept for A/B runs);
 //   * column sums live in registers in 16-bit lanes (r | b << 16, g); the last n output rows are
 //     smem rings private to each lane (no synchronisation); rows without a mask pixel in the strip
 //     (the common case) take a short path: fg = quotient, bg = copy of the input row.
 // Two forms share the arithmetic and the mailbox protocol (launch_opt_iir_warp picks by batch size): k_opt_iir_w, one
 // warp per strip as described above, and k_opt_iir_w3 (further down), where the two layers of a strip run on two warps
 // fed by a producer thread -- shorter row steps for machines that are not full.
+// Followers: with IirWParams::progress set, every strip publishes (st.release.gpu, every 64 rows -- by lane 0 after the
+// bulk stores of those rows have completed, in the trio form by the producer thread) how many of its bg rows are
+// globally visible, and every CTA executes griddepcontrol.launch_dependents once it is set up: the bg thumbnail pass
+// (resample.cu, FOLLOW form), launched behind this kernel with programmatic stream serialization, becomes resident
+// beside it only after every CTA of this grid has started -- it fills the issue slots this latency-bound kernel
+// leaves idle and can never starve the strips it waits for.
 // The truncating division is one multiply-high: floor(num/den) = umulhi(2*num, ceil(2^31/den)),
 // exact for num <= 255*den, den <= 500; records of fg pixels arrive pre-doubled in 16-bit lanes
 // (optimise_firw.cu) so that numerator assembly is one multiply-add per word.

@@ -1,4 +1,4 @@
-// resample.cu -- k_reduce_box / k_resample_h / k_resample_v: PIL Image.thumbnail at
+// resample.cu -- k_resample_tile / k_reduce_box / k_resample_h / k_resample_v: PIL Image.thumbnail at
 // internetarchivepdf/mrc.py:420-434 (fg) and :454-468 (bg).
 //
 // Pillow 12.2 semantics restated (oracle/mrc_oracle.c orc_resample / orc_reduce and
@@ -11,6 +11,10 @@
 //   out = clip8((2^21 + sum p*k) >> 22).
 // The size logic and the coefficient tables are computed on the host once per plan (they depend
 // only on the shapes); the kernels are pure gather-multiply-accumulate byte kernels.
+// Integer shrink factors without a box reduce (the bg/3 case of the hot path) take k_resample_tile: both passes of a
+// 32 x 32 output tile in one CTA, the uint8 intermediate in shared memory.  Its FOLLOW form is launched behind the
+// optimise sweep as a programmatic dependent and consumes bg rows while the sweep still writes later ones
+// (launch_resample_follow; the sweep publishes per-strip row progress, optimise_warp.cu).
 #include "common.cuh"
 #include "tma.cuh"
 #include <cmath>

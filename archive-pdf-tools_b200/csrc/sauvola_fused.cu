@@ -9,17 +9,21 @@
 //   * the source rows (RGB or gray) arrive by TMA bulk copies (cp.async.bulk, one row segment per copy, NS rows in
 //     flight, one mbarrier per stage) issued by one elected thread; threads read their 24 / 8 bytes with 64-bit LDS;
 //   * RGB -> L is two dp4a per pixel on the coefficient bytes (exact: 19595 = 76*256 + 139 ...); the blur's vertical pass
-//     runs on a (2R+1)-row register window (R <= 2), its float32 results cross threads through a double-buffered smem
-//     row, the horizontal pass + uint8 truncation give the final gray row -- FP64, scipy's operation order, no FMA;
+//     runs on a (2R+1)-row register window (R <= 2) over the thread's 8 columns plus R neighbour columns on either side
+//     (warp shuffles; the edge lanes of a warp read them from the stage), so the horizontal pass + uint8 truncation
+//     need no exchange through shared memory -- FP64, scipy's operation order, no FMA;
 //   * that row enters the running column sums (sum, sum of squares) straight from registers and is also written to a
 //     gray "delay line" plane, from which the SAME thread re-reads it as the current row (u rows later) and as the row
-//     leaving the window (window rows later): L2-resident re-reads, 64-bit loads two rows ahead of use;
+//     leaving the window (window rows later): L2-resident re-reads, 64-bit loads issued an iteration ahead of use;
 //   * horizontal window sums are differences of a CTA-wide prefix of the column sums: thread-local prefix -> warp
-//     shuffle scan -> warp totals through smem; the CTA-wide prefix is published AFTER the row's single barrier for the
-//     row that follows, so one barrier per row serves the blur exchange, the warp totals and the prefix hand-over;
-//   * S/n and Q/n are multiply-high + shift with a per-row magic number (exact, see fast_div_ok), the test runs in FP64
-//     (__dmul_rn/__dadd_rn, the reference's operation order); edge columns (clamped windows) take the FP64-reciprocal
-//     form of sauvola.cu.
+//     shuffle scan -> warp totals through smem -> prefix published to a ring of three smem buffers.  The one CTA-wide
+//     synchronisation per row is a SPLIT mbarrier: a warp arrives right after publishing its total and waits only
+//     before it needs the others', with gray production and the test of the previous row in between;
+//   * S/n and Q/n are multiply-high + shift with a per-row magic number (exact, see fast_div_ok; columns whose window
+//     the page clamps read per-pixel magics from a row-invariant smem table), and the decision is ONE 16-bit table
+//     lookup + integer compare: the reference's FP64 test is a monotone function of the integer variance for given
+//     (mean, pixel), tabulated exactly once per (k, R) by k_sauvola_vmin.  Page corners (windows clamped both ways) and
+//     windows too large for the 32-bit magic run the FP64 sequence itself (__dmul_rn/__dadd_rn, reference order).
 // Pages whose blur radius exceeds 2 (sigma_est >= 22.5) are pre-blurred into the gray plane by gray_blur.cu's tiled
 // kernels and thresholded from there (no production step).  Algorithmic HBM bytes: C in + 1 out per pixel.
 #include "common.cuh"
