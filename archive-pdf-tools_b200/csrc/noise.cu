@@ -11,15 +11,18 @@
 //                    float32 accumulation order of PyWavelets' convolution is kept with
 //                    __fmul_rn/__fadd_rn (no FMA); |dd| is stored as its IEEE bit pattern
 //                    (monotone as uint32 for non-negative floats), 0 for dd == 0.
-//   k_noise_select : one CTA per page, exact order statistics by 3-pass radix select
+//   k_noise_select : one thread-block cluster (1..8 CTAs, histograms summed through distributed shared memory) per page,
+//                    exact order statistics by 3-pass radix select
 //                    (12 + 10 + 10 bits) over smem histograms; both middle ranks are tracked
 //                    so an even count reproduces np.median's float32 mean of two.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <math_constants.h>
 #include <cstdlib>
 
 namespace b200mrc {
 namespace {
+namespace cg = cooperative_groups;
 
 struct NoiseParams {
     const uint8_t *in; int64_t in_pitch, in_stride; int C;
@@ -166,27 +169,53 @@ __device__ void block_find_rank(const uint32_t *hist, int nbins, uint32_t rank, 
     __syncthreads();
 }
 
+// A page is served by a thread-block CLUSTER of 1, 2, 4 or 8 CTAs (as many as keep every SM busy: 64 pages -> 2, 16
+// pages -> 8): each CTA histograms its share of the page's keys in its own shared memory, and after every pass all CTAs
+// sum the cluster's histograms through distributed shared memory -- every CTA then holds the page's histogram and takes
+// the same decisions, so nothing is broadcast.
 __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
 {
     __shared__ uint32_t hist[2][4096];
     __shared__ uint32_t s_scan[32];
     __shared__ uint32_t s_res[2];
-    const int page = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CS = cluster.num_blocks(), cr = cluster.block_rank();
+    const int page = blockIdx.x / CS, tid = threadIdx.x;
     const int64_t total = ((int64_t)p.oh * p.ow + 3) & ~3ll;          // per-page key stride: padded with zeros to 4
     const uint32_t *keys = p.keys + (int64_t)page * total;
+    // this CTA's share of the keys: [k_lo, k_hi), multiples of 4
+    const int64_t share = ((total / 4 + CS - 1) / CS) * 4;
+    const int64_t k_lo = min(total, (int64_t)cr * share), k_hi = min(total, k_lo + share);
+    // hist <- sum over the cluster's CTAs (all 2 x 4096 bins; 8 per thread): read everyone's, then replace one's own
+    auto cluster_sum = [&]() {
+        if (CS == 1) { __syncthreads(); return; }
+        cluster.sync();                                      // every CTA's local histogram is complete
+        uint32_t acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0;
+        for (unsigned r = 0; r < CS; r++) {
+            const uint32_t *h = cluster.map_shared_rank(&hist[0][0], r);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += h[tid + j * SEL_T];
+        }
+        cluster.sync();                                      // everyone has read: the local copies may be replaced
+#pragma unroll
+        for (int j = 0; j < 8; j++) (&hist[0][0])[tid + j * SEL_T] = acc[j];
+        __syncthreads();
+    };
 
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
     // pass 1: top 12 bits (non-zero keys only)
-    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+    for (int64_t i = k_lo + (int64_t)tid * 4; i < k_hi; i += SEL_T * 8) {
         const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
         const int64_t i2 = i + SEL_T * 4;
-        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint4 b = i2 < k_hi ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
         const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int q = 0; q < 8; q++) if (kk[q]) atomicAdd(&hist[0][kk[q] >> 20], 1u);
     }
-    __syncthreads();
+    cluster_sum();
     uint32_t cnt;
     {
         // total count of non-zero keys = rank of the (virtual) end
@@ -201,8 +230,8 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
         cnt = v;
         __syncthreads();
     }
-    if (cnt == 0) {
-        if (tid == 0) p.sigma_out[page] = CUDART_NAN;
+    if (cnt == 0) {                                          // the same in every CTA of the cluster
+        if (tid == 0 && cr == 0) p.sigma_out[page] = CUDART_NAN;
         return;
     }
     uint32_t rk[2] = {(cnt - 1) / 2, cnt / 2};
@@ -215,10 +244,10 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
     // pass 2: middle 10 bits under each target prefix
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+    for (int64_t i = k_lo + (int64_t)tid * 4; i < k_hi; i += SEL_T * 8) {
         const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
         const int64_t i2 = i + SEL_T * 4;
-        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint4 b = i2 < k_hi ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
         const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -229,7 +258,7 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
             if (top == pre[1]) atomicAdd(&hist[1][mid], 1u);
         }
     }
-    __syncthreads();
+    cluster_sum();
     for (int t = 0; t < 2; t++) {
         uint32_t b, r;
         block_find_rank(hist[t], 1024, rk[t], s_scan, s_res, b, r);
@@ -238,10 +267,10 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
     // pass 3: low 10 bits
     for (int i = tid; i < 2 * 4096; i += SEL_T) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)tid * 4; i < total; i += SEL_T * 8) {
+    for (int64_t i = k_lo + (int64_t)tid * 4; i < k_hi; i += SEL_T * 8) {
         const uint4 a = *reinterpret_cast<const uint4 *>(keys + i);
         const int64_t i2 = i + SEL_T * 4;
-        const uint4 b = i2 < total ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
+        const uint4 b = i2 < k_hi ? *reinterpret_cast<const uint4 *>(keys + i2) : make_uint4(0, 0, 0, 0);
         const uint32_t kk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -252,13 +281,13 @@ __global__ void __launch_bounds__(SEL_T) k_noise_select(const NoiseParams p)
             if (hi == pre[1]) atomicAdd(&hist[1][lo], 1u);
         }
     }
-    __syncthreads();
+    cluster_sum();
     for (int t = 0; t < 2; t++) {
         uint32_t b, r;
         block_find_rank(hist[t], 1024, rk[t], s_scan, s_res, b, r);
         pre[t] = (pre[t] << 10) | b;
     }
-    if (tid == 0) {
+    if (tid == 0 && cr == 0) {
         const float a = __uint_as_float(pre[0]), b = __uint_as_float(pre[1]);
         const float med = (cnt & 1u) ? a : __fdiv_rn(__fadd_rn(a, b), 2.0f);   // np.median (float32)
         p.sigma_out[page] = __ddiv_rn((double)med, 0.6744897501960817);
@@ -303,8 +332,21 @@ int launch_estimate_noise(const uint8_t *in, int64_t in_pitch, int64_t in_stride
         { ProfScope _ps("k_noise_dd_march", st); k_noise_dd_march<<<grid, 128, 0, st>>>(p); }
     }
     B200MRC_LAUNCH_CHECK();
-    { ProfScope _ps("k_noise_select", st); k_noise_select<<<N, SEL_T, 0, st>>>(p); }
-    B200MRC_LAUNCH_CHECK();
+    {
+        // CTAs per page: the largest cluster (<= 8, the portable limit) that still fits every page's cluster on the GPU at once
+        int cs = 1;
+        while (cs < 8 && (int64_t)N * cs * 2 <= dev_info().sm_count) cs *= 2;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(N * cs)); cfg.blockDim = dim3(SEL_T); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        void *args[] = {(void *)&p};
+        ProfScope _ps("k_noise_select", st);
+        B200MRC_CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)k_noise_select, args));
+    }
+    count_launch();
     return B200MRC_OK;
 }
 
