@@ -51,7 +51,7 @@ enum TuneKey {
     T_FIRW_WPC,         // FIR pass: warps per CTA
     T_FUSED_NT,         // fused threshold: threads per CTA (0 auto, 128 | 192 | 256)
     T_FUSED_BANDS,      // fused threshold: row bands per strip (0 auto)
-    T_FUSED_DBG,        // fused threshold: timing experiments (skip parts of the kernel; results are wrong)
+    T_FUSED_DBG,        // fused threshold: timing experiments; honoured only by builds with -DB200MRC_EXPERIMENTS (results are wrong)
     T_FUSED_OCC,        // fused threshold, 128-thread CTAs: CTAs per SM the kernel is compiled for (0 = 4; 3 | 5)
     T_THRESHOLD_PATH,   // 0 auto (fused where it applies), 1 two-pass (gray_blur + sauvola kernels), 2 fused      env: legacy | fused
     T_OPT_PATH,         // 0 split (FIR + sweep), 1 generic fused sweep                                    env: generic

@@ -62,7 +62,7 @@ struct FusedParams {
     const uint16_t *vmin;               // decision table (below): pixel p with window mean m is foreground iff variance >= vmin[m << 8 | p]
     int flags;
     int out8;                                                   // out rows allow 8-byte stores
-    int dbg;                                                    // FUSED_DBG = 1: skip the per-pixel test (timing experiments only; the mask is wrong)
+    int dbg;                                                    // 1: skip the per-pixel test (timing experiments, -DB200MRC_EXPERIMENTS builds only; always 0 otherwise)
     // byte offsets, inside one prefix buffer and relative to the thread's slot, of the entries a thread publishes
     // (st) and of the two window-edge entries of each of its 8 pixels (hi, lo): uniform values, so the shared-memory
     // accesses take them from the uniform register file
@@ -677,7 +677,11 @@ int launch_sauvola_fused(const uint8_t *src, int64_t src_pitch, int64_t src_stri
     p.km1 = k - 1.0;
     p.k2 = k * k / Rr / Rr;                                       // sauvola.pyx:60
     p.flags = flags;
-    p.dbg = tune(T_FUSED_DBG);
+#ifdef B200MRC_EXPERIMENTS
+    p.dbg = tune(T_FUSED_DBG);                                    // timing experiments: builds with -DB200MRC_EXPERIMENTS only
+#else
+    p.dbg = 0;                                                    // a shipped library never skips the test, whatever the knob says
+#endif
     p.out8 = !(((uintptr_t)out & 7) || (out_pitch & 7) || (out_stride & 7));
 
     const FusedSmem L(nt, C, p.eb);
