@@ -520,7 +520,9 @@ class StreamedDecomposer:
                     dst = out['mask_packed'] if (name == 'mask' and self.host_unpack) else out[name]
                     dst[lo:hi].copy_((st if st is not None else plane.t)[:m], non_blocking=True)
                     if name == 'mask' and self.host_unpack:
-                        futures.append(self.pool.submit(self._unpack, self.s_out.record_event(), out, lo, hi))
+                        landed = torch.cuda.Event(blocking=True)   # the worker sleeps on it instead of spinning on a core
+                        landed.record(self.s_out)
+                        futures.append(self.pool.submit(self._unpack, landed, out, lo, hi))
                 out_done[i] = self.s_out.record_event()
             tail_cmp[slot], tail_out[slot] = cmp_done[i], out_done[i]
         self._tail_cmp, self._tail_out = tail_cmp, tail_out
