@@ -347,8 +347,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'                       # keep NCCL's version banner off stdout: one JSON line only
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # NCCL's banner / debug lines go to stderr: stdout carries the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import archive_pdf_tools_b200 as pkg
     from archive_pdf_tools_b200 import _lib
