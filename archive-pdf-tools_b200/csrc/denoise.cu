@@ -271,6 +271,28 @@ __global__ void __launch_bounds__(DT) k_mask_denoise(const DenoiseParams p)
     }
 }
 
+// ---- any (mincnt, n_size): the same fixed point, byte planes, one thread per pixel.  The reference only ever calls
+// (4, 2) (mrc.py:388), which is the bit-sliced kernel above; this form completes the Cython signature
+// fast_mask_denoise(mask, w, h, mincnt, n_size) (optimiser.pyx:436).  r starts as the mask itself and pixels only ever go
+// 1 -> 0, decided from counts that are never below the true ones (stale neighbours are still set), so updating in place
+// in any order converges to the sequential result; a pass that clears nothing ends the iteration (host loop).
+__global__ void __launch_bounds__(256) k_mask_denoise_general(uint8_t *mask, int64_t pitch, int64_t stride, const uint8_t *m0,
+                                                              int W, int H, int mincnt, int n, unsigned *changed)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), page = blockIdx.z;
+    if (x < n || x >= W - n || y < n || y >= H - n) return;
+    uint8_t *r = mask + (int64_t)page * stride;
+    const uint8_t *m = m0 + (int64_t)page * H * W;
+    if (!r[(int64_t)y * pitch + x]) return;
+    int cnt = 0;                                             // earlier neighbours: their current value; later ones: the input
+    for (int dy = -n; dy <= n; dy++)
+        for (int dx = -n; dx <= n; dx++) {
+            if (dy < 0 || (dy == 0 && dx < 0)) cnt += r[(int64_t)(y + dy) * pitch + x + dx] ? 1 : 0;
+            else if (dy > 0 || dx > 0) cnt += m[(int64_t)(y + dy) * W + x + dx] ? 1 : 0;
+        }
+    if (cnt < mincnt) { r[(int64_t)y * pitch + x] = 0; *changed = 1u; }
+}
+
 struct DenoiseLayout {
     int Ww, tiles_x, tiles_y;
     size_t off_Mb, off_Rb, off_flags, off_sync, total;
@@ -340,7 +362,37 @@ extern "C" int b200mrc_denoise(uint8_t *mask, int64_t pitch, int64_t page_stride
                                void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!mask || width <= 0 || height <= 0 || n_pages <= 0) return B200MRC_ERR_INVALID;
-    if (mincnt != 4 || n_size != 2) return B200MRC_ERR_UNSUPPORTED;
+    if (mincnt != 4 || n_size != 2) {
+        // general form: stream-ordered temporaries, one launch per pass, a host check of the "changed" word after each
+        if (n_size < 0 || n_size > 64 || pitch < width || n_pages > 65535 || (height + 7) / 8 > 65535) return B200MRC_ERR_UNSUPPORTED;
+        if (width <= 2 * n_size || height <= 2 * n_size) return B200MRC_OK;          // no interior pixel
+        cudaStream_t st = (cudaStream_t)stream;
+        uint8_t *m0 = nullptr;
+        unsigned *chg = nullptr;
+        const size_t page_bytes = (size_t)width * height;
+        B200MRC_CUDA_TRY(cudaMallocAsync((void **)&m0, page_bytes * n_pages + 256, st));
+        chg = (unsigned *)(m0 + ((page_bytes * n_pages + 15) & ~(size_t)15));
+        int rc = B200MRC_OK;
+        cudaError_t e = cudaMemcpy2DAsync(m0, width, mask, pitch, width, (size_t)height, cudaMemcpyDeviceToDevice, st);
+        for (int pg = 1; pg < n_pages && e == cudaSuccess; pg++)
+            e = cudaMemcpy2DAsync(m0 + pg * page_bytes, width, mask + (int64_t)pg * page_stride, pitch, width, (size_t)height, cudaMemcpyDeviceToDevice, st);
+        const dim3 grid(cdiv(width, 32), cdiv(height, 8), n_pages);
+        while (e == cudaSuccess) {
+            unsigned h = 0;
+            e = cudaMemsetAsync(chg, 0, sizeof(unsigned), st);
+            if (e != cudaSuccess) break;
+            { ProfScope _ps("k_mask_denoise_general", st);
+              k_mask_denoise_general<<<grid, 256, 0, st>>>(mask, pitch, page_stride, m0, width, height, mincnt, n_size, chg); }
+            count_launch();
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&h, chg, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess || !h) break;
+        }
+        if (e != cudaSuccess) rc = (int)e;
+        cudaFreeAsync(m0, st);
+        return rc;
+    }
     if ((pitch & 3) || ((uintptr_t)mask & 3) || (page_stride & 3) || pitch < width) return B200MRC_ERR_ALIGNMENT;
     return launch_denoise(mask, pitch, page_stride, width, height, n_pages, workspace, workspace_bytes,
                           (cudaStream_t)stream);

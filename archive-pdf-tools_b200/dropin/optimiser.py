@@ -52,8 +52,6 @@ def optimise_rgb2(mask, img, width, height, n_size):
 def fast_mask_denoise(mask, width, height, mincnt, n_size):
     """cython/optimiser.pyx:436 -- in place; returns the same array object."""
     mask = _check_u8(mask, 2)
-    if (mincnt, n_size) != (4, 2):
-        raise NotImplementedError('fast_mask_denoise is implemented for mincnt=4, n_size=2 (the only call site, mrc.py:388)')
     if width <= 0 or height <= 0:
         return mask
     eng = _pkg.get_engine()

@@ -132,9 +132,11 @@ B200MRC_API int b200mrc_threshold_mask(const uint8_t *in, int64_t in_pitch, int6
                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* A8  fast_mask_denoise (optimiser.pyx:436-472), in place, exact raster-order semantics.
- * Implemented for the only configuration the reference uses: mincnt = 4, n_size = 2
- * (mrc.py:388); anything else returns B200MRC_ERR_UNSUPPORTED.
- * workspace: b200mrc_denoise_workspace_bytes(). */
+ * mincnt = 4, n_size = 2 -- the only configuration the reference uses (mrc.py:388) -- is one persistent bit-sliced
+ * kernel on `workspace` (b200mrc_denoise_workspace_bytes()).  Any other (mincnt, 0 <= n_size <= 64) takes a general
+ * one-thread-per-pixel form of the same fixed point: stream-ordered temporaries (cudaMallocAsync, one byte per pixel), one
+ * launch per pass and a stream synchronisation after each -- it completes the Cython signature, it is not a fast path;
+ * `workspace` is not used by it. */
 B200MRC_API size_t b200mrc_denoise_workspace_bytes(int width, int height, int n_pages);
 B200MRC_API int b200mrc_denoise(uint8_t *mask, int64_t pitch, int64_t page_stride,
                     int width, int height, int n_pages, int mincnt, int n_size,

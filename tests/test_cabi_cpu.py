@@ -36,7 +36,8 @@ def test_argument_validation_without_gpu():
     p = C.cast(buf, C.c_void_p)
     assert L.b200mrc_sauvola(p, 8, 64, p, 8, 64, 8, 8, 1, 300, 33, 0.34, 128.0, 0, None) == _lib.ERR_UNSUPPORTED
     assert L.b200mrc_sauvola(p, 7, 64, p, 8, 64, 7, 8, 1, 33, 33, 0.34, 128.0, 0, None) == _lib.ERR_ALIGNMENT
-    assert L.b200mrc_denoise(p, 8, 64, 8, 8, 1, 3, 2, None, 0, None) == _lib.ERR_UNSUPPORTED
+    assert L.b200mrc_denoise(p, 8, 64, 8, 8, 1, 3, 65, None, 0, None) == _lib.ERR_UNSUPPORTED    # n_size beyond the general form's range
+    assert L.b200mrc_denoise(p, 8, 64, 8, 8, 1, 3, 4, None, 0, None) == 0                        # 8x8 page, n_size 4: no interior pixel, nothing to do
     assert L.b200mrc_optimise(p, 8, 64, p, 8, 64, 1, p, 8, 64, 17, None, 0, 0, 10, 8, 8, 1, None, 0, None) == _lib.ERR_UNSUPPORTED
     assert L.b200mrc_noise_workspace_bytes(2550, 3300, 1) >= 4 * 826 * 639
     assert L.b200mrc_denoise_workspace_bytes(2550, 3300, 64) > 0

@@ -132,6 +132,26 @@ def test_denoise_matches_oracle(eng, orc, shape):
         assert np.array_equal(got[i], exp), (shape, i, int((got[i] != exp).sum()))
 
 
+@pytest.mark.parametrize('mincnt,n_size', [(1, 1), (5, 1), (8, 3), (12, 2), (0, 2), (1, 0), (40, 4)])
+def test_denoise_general_parameters_match_oracle(eng, orc, mincnt, n_size):
+    """fast_mask_denoise(mask, w, h, mincnt, n_size) for parameters the reference never uses: the general
+    one-thread-per-pixel form of the same fixed point (several pages, a pitched plane, a cascade)."""
+    rng = np.random.default_rng(mincnt * 10 + n_size)
+    h, w = 83, 131
+    ms = [rng.random((h, w)) < d for d in (0.05, 0.3, 0.6, 0.95)]
+    diag = np.zeros((h, w), bool)
+    idx = np.arange(min(h, w))
+    diag[idx, idx] = True; diag[idx[:-1], idx[:-1] + 1] = True
+    ms.append(diag)
+    ms = np.stack(ms)
+    pl = _plane(eng, ms)
+    eng.denoise(pl, mincnt, n_size)
+    got = pl.numpy(np.bool_)
+    for i in range(len(ms)):
+        exp = orc.denoise(ms[i], mincnt, n_size)
+        assert np.array_equal(got[i], exp), (mincnt, n_size, i, int((got[i] != exp).sum()))
+
+
 def test_denoise_long_cascade(eng, orc):
     # a 2-px diagonal band: every removal exposes the next pixel -> O(H) dependency chain across tiles
     h, w = 700, 700

@@ -154,6 +154,12 @@ def test_dropin_modules_match_reference_cython(eng, refmods):
     ret = optimiser.fast_mask_denoise(a, w, h, 4, 2)
     ropt.fast_mask_denoise(b, w, h, 4, 2)
     assert ret is a and np.array_equal(a.view(np.uint8), b)
+    dense = rng.random((h, w)) < 0.35
+    for mincnt, n_size in [(1, 1), (3, 1), (8, 3), (24, 2), (0, 2), (2, 0), (60, 5)]:   # the general form: any (mincnt, n_size)
+        a = dense.copy(); b = dense.copy().view(np.uint8)
+        assert optimiser.fast_mask_denoise(a, w, h, mincnt, n_size) is a
+        ropt.fast_mask_denoise(b, w, h, mincnt, n_size)
+        assert np.array_equal(a.view(np.uint8), b), (mincnt, n_size, int((a.view(np.uint8) != b).sum()))
     with pytest.raises(ValueError):
         optimiser.optimise_gray2(mask, img.astype(np.float32), w, h, 3)
 
