@@ -31,11 +31,12 @@ def have_ref():
     return all(os.path.exists(ref_so_path(n)) for n in ('sauvola', 'optimiser'))
 
 
-# The reference's Python glue as byte code: internetarchivepdf/{mrc,const,jpeg2000}.py compiled (py_compile, unmodified)
+# The reference's Python glue as byte code: internetarchivepdf/{mrc,const,jpeg2000,recode}.py compiled (py_compile, unmodified)
 # into oracle/_ref/internetarchivepdf/*.pyc, so that the GPU box -- where /root/reference does not exist -- can run the
 # UNMODIFIED reference create_mrc_hocr_components on top of the drop-in `sauvola` / `optimiser` modules
-# (tests/test_gpu_pipeline.py::test_unmodified_reference_through_install).  Built artefacts only; no source is copied.
-GLUE = ('mrc', 'const', 'jpeg2000')
+# (tests/test_gpu_pipeline.py::test_unmodified_reference_through_install) and the page loop of recode.py around it
+# (::test_reference_recode_page_loop_on_the_dropin).  Built artefacts only; no source is copied.
+GLUE = ('mrc', 'const', 'jpeg2000', 'recode')
 GLUE_DIR = os.path.join(OUT, 'internetarchivepdf')
 
 

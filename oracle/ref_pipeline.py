@@ -183,3 +183,64 @@ def _load_reference_mrc(reference_dir, dropin):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def load_reference_recode(mrc_module, reference_dir='/root/reference'):
+    """Import the UNMODIFIED reference internetarchivepdf/recode.py (the checkout, or the byte-compiled glue on the GPU
+    box) bound to `mrc_module` as internetarchivepdf.mrc.  Everything else recode.py imports and this image lacks --
+    fitz, hocr.parse, pdfhacks, pdfrenderer, scandata -- is a stub: the tests drive insert_images_mrc (recode.py:266-530),
+    whose page loop needs only the four hocr.parse names (given by the caller through `hocr_pages`) and page objects."""
+    pkg_dir = os.path.join(reference_dir, 'internetarchivepdf')
+    path = os.path.join(pkg_dir, 'recode.py')
+    if not os.path.exists(path):
+        if not build_ref.have_glue():
+            return None
+        pkg_dir = build_ref.GLUE_DIR
+        path = os.path.join(pkg_dir, 'recode.pyc')
+    names = ('fitz', 'hocr', 'hocr.parse', 'internetarchivepdf', 'internetarchivepdf.mrc', 'internetarchivepdf.grayconvert',
+             'internetarchivepdf.pdfhacks', 'internetarchivepdf.pdfrenderer', 'internetarchivepdf.scandata',
+             'internetarchivepdf.jpeg2000', 'internetarchivepdf.const')
+    saved = {k: sys.modules.get(k) for k in names}
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    def unused(*_a, **_k):
+        raise NotImplementedError('stub: not on the page loop')
+
+    stub('fitz', TOOLS=types.SimpleNamespace(set_icc=lambda *_: None))
+    stub('hocr')
+    # a "hocr page" is a dict here: {'dpi': (x, y) or None, 'words': hocr_word_data, 'dim': (w, h)}
+    stub('hocr.parse', hocr_page_iterator=lambda pages: iter(pages), hocr_page_to_word_data=lambda p: p['words'],
+         hocr_page_get_dimensions=lambda p: p['dim'], hocr_page_get_scan_res=lambda p: p.get('dpi') or (None, None))
+    pkg = types.ModuleType('internetarchivepdf')
+    pkg.__path__ = [pkg_dir]
+    sys.modules['internetarchivepdf'] = pkg
+    sys.modules['internetarchivepdf.mrc'] = mrc_module
+    stub('internetarchivepdf.grayconvert', special_gray_convert=unused)
+    stub('internetarchivepdf.pdfhacks', **{n: unused for n in ('fast_insert_image', 'write_pdfa', 'write_page_labels',
+                                                               'write_basic_ua', 'write_metadata', 'write_pdf_toc')})
+    stub('internetarchivepdf.pdfrenderer', TessPDFRenderer=unused)
+    stub('internetarchivepdf.scandata', **{n: unused for n in ('scandata_xml_get_skip_pages', 'scandata_xml_get_page_numbers',
+                                                               'scandata_xml_get_dpi_per_page', 'scandata_xml_get_document_dpi')})
+    try:
+        if path.endswith('.pyc'):
+            loader = importlib.machinery.SourcelessFileLoader('internetarchivepdf.recode', path)
+            spec = importlib.util.spec_from_loader('internetarchivepdf.recode', loader, origin=path)
+        else:
+            spec = importlib.util.spec_from_file_location('internetarchivepdf.recode', path)
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spec.loader.exec_module(mod)                     # jpeg2000 / const come from pkg_dir (real reference code)
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

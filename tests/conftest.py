@@ -99,3 +99,51 @@ def tuning():
     yield set_
     for k, v in saved.items():
         _lib.set_tuning(k, v)
+
+
+def drive_reference_page_loop(recode, pages, hocr_words, tmp_path, dpi, force_1bit=False, **mrc_kw):
+    """Run the UNMODIFIED reference page loop recode.insert_images_mrc (recode.py:266-530) over `pages` (numpy arrays,
+    written as PNG files) with PDF objects and encoders mocked: pages are plain recorders of insert_image(), and
+    encode_mrc_images / encode_mrc_mask (mrc.py:474-580; external jbig2 / JPEG2000 tools) hand the arrays they are given
+    to the test instead of encoding them.  Returns (captured arrays per page, page recorders, timing keys seen)."""
+    from PIL import Image
+    captured, files = [], []
+    for i, pg in enumerate(pages):
+        f = str(tmp_path / ('page%03d.png' % i))
+        Image.fromarray(pg).save(f)
+        files.append(f)
+
+    class Page:
+        rect = (0, 0, 612, 792)
+
+        def __init__(self):
+            self.inserted = []
+
+        def insert_image(self, rect, **kw):
+            self.inserted.append(kw)
+
+    def dummy(tag):
+        f = str(tmp_path / ('%s_%d.bin' % (tag, len(captured))))
+        open(f, 'wb').write(b'x')
+        return f
+
+    def fake_encode_mrc_images(mrc_gen, **kw):
+        mask, fg, bg = list(mrc_gen)                          # the reference's own consumer pulls the three yields in order
+        captured.append(dict(mask=mask, fg=fg, bg=bg))
+        return dummy('mask'), dummy('bg'), (bg.shape[1], bg.shape[0]), dummy('fg'), (fg.shape[1], fg.shape[0])
+
+    def fake_encode_mrc_mask(np_mask, **kw):
+        captured.append(dict(mask_inverted=np_mask))
+        return dummy('jb2'), dummy('png')
+
+    saved = recode.encode_mrc_images, recode.encode_mrc_mask
+    recode.encode_mrc_images, recode.encode_mrc_mask = fake_encode_mrc_images, fake_encode_mrc_mask
+    try:
+        to_pdf = [Page() for _ in pages]
+        hocr_pages = [dict(dpi=None, words=w, dim=(p.shape[1], p.shape[0])) for p, w in zip(pages, hocr_words)]
+        errors = set()
+        recode.insert_images_mrc(to_pdf, hocr_pages, image_files=files, dpi=dpi, hq_pages=[False] * len(pages),
+                                 tmp_dir=str(tmp_path), force_1bit_output=force_1bit, errors=errors, **mrc_kw)
+    finally:
+        recode.encode_mrc_images, recode.encode_mrc_mask = saved
+    return captured, to_pdf, errors

@@ -408,6 +408,50 @@ def test_unmodified_reference_through_install(eng, synth, orc, name):
     assert [k for k, _ in timing] == g['timing_keys']
 
 
+@pytest.mark.parametrize('binding', ['dropin-modules', 'install-rebinds-mrc'])
+def test_reference_recode_page_loop_on_the_dropin(eng, synth, tmp_path, binding):
+    """The reference's page loop itself -- the UNMODIFIED recode.insert_images_mrc (recode.py:266-530: image loading, the
+    create_mrc_hocr_components call sites at :400-406 (1-bit output) and :427-433 (full MRC), the encoder and PDF calls,
+    here mocked) -- running on this engine, both ways a maintainer can switch: (a) install() only publishes the GPU
+    `sauvola` / `optimiser` modules under the reference's mrc.py; (b) install() rebinds create_mrc_hocr_components in the
+    imported internetarchivepdf.mrc before recode.py binds it by name (recode.py:39-40)."""
+    import sys
+    import archive_pdf_tools_b200 as pkg
+    from conftest import drive_reference_page_loop
+    from oracle import ref_pipeline
+    pkg.install(patch_reference=False)
+    mrc = ref_pipeline.load_reference_mrc_on_dropin()
+    if mrc is None:
+        pytest.skip('reference glue not available (oracle/_ref/internetarchivepdf not built)')
+    if binding == 'install-rebinds-mrc':
+        sys.modules['internetarchivepdf.mrc'] = mrc
+        try:
+            pkg.install(patch_reference=True)
+        finally:
+            del sys.modules['internetarchivepdf.mrc']
+    recode = ref_pipeline.load_reference_recode(mrc)
+    if recode is None:
+        pytest.skip('reference recode glue not available')
+    if binding == 'install-rebinds-mrc':
+        assert recode.create_mrc_hocr_components is pkg.create_mrc_hocr_components
+    else:
+        assert recode.create_mrc_hocr_components.__module__ == 'internetarchivepdf.mrc' and mrc.optimise_rgb2.__module__ == 'optimiser'
+    for name in ('rgb_clean_bg3', 'gray_noisy_bg2_fg2', 'rgb_halftone_nodenoise_bg4'):
+        g = load_golden(name, synth)
+        kw = dict(bg_downsample=g['bg_downsample'], fg_downsample=g['fg_downsample'], denoise_mask=g['denoise'])
+        cap, pdf, errors = drive_reference_page_loop(recode, [g['page'], g['page']], [[], []], tmp_path, g['dpi'], **kw)
+        assert len(cap) == 2 and len(pdf[1].inserted) == 2
+        for c in cap:
+            assert np.array_equal(c['mask'], g['mask']), (name, int((c['mask'] != g['mask']).sum()))
+            assert np.array_equal(c['fg'], g['fg']) and np.array_equal(c['bg'], g['bg']), name
+        cap, pdf, errors = drive_reference_page_loop(recode, [g['page']], [[]], tmp_path, g['dpi'], force_1bit=True, **kw)
+        assert np.array_equal(cap[0]['mask_inverted'], ~g['mask']), name
+    g = load_hocr_golden('hocr_rgb_clean_bg3', synth)
+    cap, pdf, errors = drive_reference_page_loop(recode, [g['page']], [g['hocr']], tmp_path, g['dpi'], downsample=g['downsample'],
+                                                 bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'])
+    assert np.array_equal(cap[0]['mask'], g['mask']) and np.array_equal(cap[0]['fg'], g['fg']) and np.array_equal(cap[0]['bg'], g['bg'])
+
+
 def test_install_rebinds_an_imported_reference(eng, synth):
     """install(patch_reference=True) with internetarchivepdf.mrc already imported: its pixel-path names are rebound."""
     import sys

@@ -270,3 +270,26 @@ def test_special_gray_logic_equals_the_imported_reference(orc, synth):
         exp = ref.special_gray_convert(img.copy())
         got = orc.special_gray_convert(img)
         assert np.array_equal(got, exp), int((got != exp).sum())
+
+
+def test_reference_page_loop_harness_reproduces_the_goldens(synth, tmp_path):
+    """The harness that drives the unmodified reference recode.insert_images_mrc (used on the GPU box against the drop-in)
+    is checked here against the reference's own Cython: it must reproduce the golden fixtures."""
+    from conftest import drive_reference_page_loop, load_golden
+    from oracle import ref_pipeline
+    if ref_pipeline.ref_modules() is None:
+        pytest.skip('oracle/_ref not built')
+    mrc = ref_pipeline.load_reference_mrc()
+    if mrc is None:
+        pytest.skip('reference checkout not available')
+    recode = ref_pipeline.load_reference_recode(mrc)
+    assert recode.create_mrc_hocr_components is mrc.create_mrc_hocr_components
+    g = load_golden('rgb_clean_bg3', synth)
+    cap, pdf, errors = drive_reference_page_loop(recode, [g['page']], [[]], tmp_path, g['dpi'], bg_downsample=g['bg_downsample'],
+                                                 fg_downsample=g['fg_downsample'], denoise_mask=g['denoise'])
+    assert len(cap) == 1 and np.array_equal(cap[0]['mask'], g['mask'])
+    assert np.array_equal(cap[0]['fg'], g['fg']) and np.array_equal(cap[0]['bg'], g['bg'])
+    assert len(pdf[0].inserted) == 2 and pdf[0].inserted[1]['overlay'] is True     # bg, then fg + mask on top (recode.py:466-482)
+    cap, pdf, errors = drive_reference_page_loop(recode, [g['page']], [[]], tmp_path, g['dpi'], force_1bit=True,
+                                                 bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'])
+    assert np.array_equal(cap[0]['mask_inverted'], ~g['mask'])                     # recode.py:407-408
