@@ -125,6 +125,22 @@ def test_full_size_400dpi_page_matches_oracle(eng, synth, orc):
     assert np.array_equal(res['fg'][0][m], pages[0][m])
 
 
+def test_config3_full_size_book_pages_match_oracle(eng, synth, orc):
+    """BASELINE config 3 shape: 3300x2550 RGB @300 DPI (window 75), halftone pages mixed with text pages in one batch
+    (their sigma_est puts them on the tiled pre-blur + direct-mode threshold, the others on the fused in-kernel blur)."""
+    import archive_pdf_tools_b200 as pkg
+    pages = np.stack([synth.make_page(20240000 + i, 3300, 2550, dpi=300, halftone=(i != 1)) for i in range(3)])
+    res = pkg.decompose_pages(pages, dpi=300, bg_downsample=3, denoise_mask='fast')
+    radii = set()
+    for i in range(3):
+        exp = orc.decompose(pages[i], dpi=300, bg_downsample=3, denoise_mask='fast')
+        assert res['sigma'][i] == exp['sigma']
+        radii.add(int(0.4 * exp['sigma'] + 0.5) if exp['sigma'] > 1.0 else 0)
+        assert np.array_equal(res['mask'][i], exp['mask']), (i, int((res['mask'][i] != exp['mask']).sum()))
+        assert np.array_equal(res['fg'][i], exp['fg']) and np.array_equal(res['bg'][i], exp['bg']), i
+    assert len(radii) > 1, radii                              # the batch really mixes blur radii
+
+
 def test_config1_window33_full_page(eng, synth, orc):
     import archive_pdf_tools_b200 as pkg
     page = synth.make_page(0, 3300, 2550, dpi=400, rgb=False)
