@@ -40,8 +40,13 @@ GLUE = ('mrc', 'const', 'jpeg2000', 'recode')
 GLUE_DIR = os.path.join(OUT, 'internetarchivepdf')
 
 
+# ... and the reference's bin/compress-pdf-images script (a second caller of create_mrc_hocr_components, :66-70)
+SCRIPT_SRC = os.path.join(REF, 'bin', 'compress-pdf-images')
+SCRIPT_PYC = os.path.join(OUT, 'bin', 'compress_pdf_images.pyc')
+
+
 def have_glue():
-    return all(os.path.exists(os.path.join(GLUE_DIR, n + '.pyc')) for n in GLUE)
+    return all(os.path.exists(os.path.join(GLUE_DIR, n + '.pyc')) for n in GLUE) and os.path.exists(SCRIPT_PYC)
 
 
 def build_glue(force=False):
@@ -54,6 +59,9 @@ def build_glue(force=False):
     os.makedirs(GLUE_DIR, exist_ok=True)
     for n, p in zip(GLUE, srcs):
         py_compile.compile(p, cfile=os.path.join(GLUE_DIR, n + '.pyc'), doraise=True)
+    if os.path.exists(SCRIPT_SRC):
+        os.makedirs(os.path.dirname(SCRIPT_PYC), exist_ok=True)
+        py_compile.compile(SCRIPT_SRC, cfile=SCRIPT_PYC, doraise=True)
     return have_glue()
 
 

@@ -244,3 +244,42 @@ def load_reference_recode(mrc_module, reference_dir='/root/reference'):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def run_reference_compress_pdf_images(mrc_module, fitz_module, argv, reference_dir='/root/reference'):
+    """Execute the UNMODIFIED reference script bin/compress-pdf-images (the checkout, or its byte code on the GPU box) as
+    __main__ with `argv`, bound to `mrc_module` as internetarchivepdf.mrc and to the caller's `fitz_module` (a fake
+    PyMuPDF: the script opens sys.argv[1] with fitz.open and walks its pages, bin/compress-pdf-images:129-148)."""
+    import marshal
+    src = os.path.join(reference_dir, 'bin', 'compress-pdf-images')
+    if os.path.exists(src):
+        code = compile(open(src).read(), src, 'exec')
+    elif os.path.exists(build_ref.SCRIPT_PYC):
+        code = marshal.loads(open(build_ref.SCRIPT_PYC, 'rb').read()[16:])
+    else:
+        return False
+    pkg_dir = os.path.join(reference_dir, 'internetarchivepdf')
+    if not os.path.exists(os.path.join(pkg_dir, 'const.py')):
+        pkg_dir = build_ref.GLUE_DIR
+    names = ('fitz', 'hocr', 'hocr.parse', 'internetarchivepdf', 'internetarchivepdf.mrc', 'internetarchivepdf.const')
+    saved = {k: sys.modules.get(k) for k in names}
+    saved_argv = sys.argv
+    hp = types.ModuleType('hocr.parse')
+    hp.hocr_page_iterator = lambda pages: iter(pages)
+    hp.hocr_page_to_word_data = lambda p: p['words']
+    pkg = types.ModuleType('internetarchivepdf')
+    pkg.__path__ = [pkg_dir]
+    sys.modules.update({'fitz': fitz_module, 'hocr': types.ModuleType('hocr'), 'hocr.parse': hp,
+                        'internetarchivepdf': pkg, 'internetarchivepdf.mrc': mrc_module})
+    sys.modules.pop('internetarchivepdf.const', None)
+    sys.argv = list(argv)
+    try:
+        exec(code, {'__name__': '__main__', '__file__': src})
+        return True
+    finally:
+        sys.argv = saved_argv
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -147,3 +147,81 @@ def drive_reference_page_loop(recode, pages, hocr_words, tmp_path, dpi, force_1b
     finally:
         recode.encode_mrc_images, recode.encode_mrc_mask = saved
     return captured, to_pdf, errors
+
+
+def run_reference_compress_script(mrc, pages, hocr_words=None):
+    """Run the UNMODIFIED reference bin/compress-pdf-images over a fake PyMuPDF document whose pages each hold one image
+    (`pages`: numpy arrays), with mrc.encode_mrc_images replaced by a recorder.  Returns (captured arrays, fake document)
+    or None when neither the reference checkout nor its byte code is available."""
+    import io, types
+    from PIL import Image
+    from oracle import ref_pipeline
+    captured = []
+
+    class Page:
+        def __init__(self, doc, xref):
+            self.doc, self.xref, self.inserted, self.cleaned = doc, xref, [], 0
+
+        def clean_contents(self):
+            self.cleaned += 1
+
+        def get_images(self, full=False):
+            return [(self.xref, 0, 0, 0, 8, 'DeviceRGB', '', 'Im%d' % self.xref, 'FlateDecode')]
+
+        def get_image_bbox(self, img_data):
+            return (0, 0, 612, 792)
+
+        def get_contents(self):
+            return [1000 + self.xref]
+
+        def read_contents(self):
+            return b'q\n/Im%d Do\nQ' % self.xref
+
+        def insert_image(self, bbox, **kw):
+            self.inserted.append(kw)
+
+    class Doc:
+        def __init__(self, path):
+            self.pages = [Page(self, i) for i in range(len(pages))]
+            self.streams, self.saved = {}, None
+
+        def __iter__(self):
+            return iter(self.pages)
+
+        def extract_image(self, xref):
+            b = io.BytesIO()
+            Image.fromarray(pages[xref]).save(b, format='PNG')
+            return {'image': b.getvalue(), 'xres': 300, 'yres': 300}
+
+        def update_stream(self, xref, data):
+            self.streams[xref] = data
+
+        def save(self, path, **kw):
+            self.saved = path
+
+    docs = []
+    fitz = types.ModuleType('fitz')
+    fitz.TOOLS = types.SimpleNamespace(set_icc=lambda *_: None)
+    fitz.open = lambda path: docs.append(Doc(path)) or docs[-1]
+
+    def fake_encode_mrc_images(mrc_gen, **kw):
+        mask, fg, bg = list(mrc_gen)
+        captured.append(dict(mask=mask, fg=fg, bg=bg))
+        import tempfile
+        fs = []
+        for _ in range(3):
+            fd, f = tempfile.mkstemp(suffix='.bin')
+            os.write(fd, b'x'); os.close(fd)
+            fs.append(f)
+        return fs[0], fs[1], (bg.shape[1], bg.shape[0]), fs[2], (fg.shape[1], fg.shape[0])
+
+    saved = mrc.encode_mrc_images
+    mrc.encode_mrc_images = fake_encode_mrc_images
+    try:
+        argv = ['compress-pdf-images', 'in.pdf', 'out.pdf'] if hocr_words is None else \
+               ['compress-pdf-images', 'in.pdf', [dict(words=w) for w in hocr_words], 'out.pdf']
+        if not ref_pipeline.run_reference_compress_pdf_images(mrc, fitz, argv):
+            return None
+    finally:
+        mrc.encode_mrc_images = saved
+    return captured, docs[0]

@@ -468,6 +468,35 @@ def test_reference_recode_page_loop_on_the_dropin(eng, synth, tmp_path, binding)
     assert np.array_equal(cap[0]['mask'], g['mask']) and np.array_equal(cap[0]['fg'], g['fg']) and np.array_equal(cap[0]['bg'], g['bg'])
 
 
+def test_reference_compress_pdf_images_script_on_the_dropin(eng, synth, orc):
+    """The reference's second caller, the script bin/compress-pdf-images (:66-70: create_mrc_hocr_components(image,
+    hocr_word_data, denoise_mask=DENOISE_FAST, bg_downsample=3), no dpi), run UNMODIFIED as __main__ over a fake PyMuPDF
+    document, on the engine's create_mrc_hocr_components (install() rebinding) -- results equal the oracle's."""
+    import sys
+    import archive_pdf_tools_b200 as pkg
+    from conftest import run_reference_compress_script
+    from oracle import ref_pipeline
+    pkg.install(patch_reference=False)
+    mrc = ref_pipeline.load_reference_mrc_on_dropin()
+    if mrc is None:
+        pytest.skip('reference glue not available')
+    sys.modules['internetarchivepdf.mrc'] = mrc
+    try:
+        pkg.install(patch_reference=True)
+    finally:
+        del sys.modules['internetarchivepdf.mrc']
+    assert mrc.create_mrc_hocr_components is pkg.create_mrc_hocr_components
+    pages = [synth.make_page(60 + i, 300, 260, dpi=100, rgb=(i != 1)) for i in range(3)]
+    out = run_reference_compress_script(mrc, pages)
+    if out is None:
+        pytest.skip('reference script byte code not available')
+    cap, doc = out
+    assert len(cap) == 3 and doc.saved == 'out.pdf' and all(len(p.inserted) == 2 for p in doc.pages)
+    for pg, c in zip(pages, cap):
+        exp = orc.decompose(pg, dpi=None, bg_downsample=3, denoise_mask='fast')
+        assert np.array_equal(c['mask'], exp['mask']) and np.array_equal(c['fg'], exp['fg']) and np.array_equal(c['bg'], exp['bg'])
+
+
 def test_install_rebinds_an_imported_reference(eng, synth):
     """install(patch_reference=True) with internetarchivepdf.mrc already imported: its pixel-path names are rebound."""
     import sys

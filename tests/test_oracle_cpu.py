@@ -293,3 +293,24 @@ def test_reference_page_loop_harness_reproduces_the_goldens(synth, tmp_path):
     cap, pdf, errors = drive_reference_page_loop(recode, [g['page']], [[]], tmp_path, g['dpi'], force_1bit=True,
                                                  bg_downsample=g['bg_downsample'], denoise_mask=g['denoise'])
     assert np.array_equal(cap[0]['mask_inverted'], ~g['mask'])                     # recode.py:407-408
+
+
+def test_reference_compress_script_harness_reproduces_the_reference(synth, tmp_path):
+    """The harness that runs the unmodified bin/compress-pdf-images (fake PyMuPDF document, encoders mocked), checked
+    here on the reference's own Cython against a direct call of the reference's create_mrc_hocr_components."""
+    from PIL import Image
+    from conftest import run_reference_compress_script
+    from oracle import ref_pipeline
+    if ref_pipeline.ref_modules() is None:
+        pytest.skip('oracle/_ref not built')
+    mrc = ref_pipeline.load_reference_mrc()
+    if mrc is None:
+        pytest.skip('reference checkout not available')
+    pages = [synth.make_page(60 + i, 150, 120, dpi=100, rgb=(i == 0)) for i in range(2)]
+    out = run_reference_compress_script(mrc, pages)
+    assert out is not None
+    cap, doc = out
+    assert len(cap) == 2 and doc.saved == 'out.pdf' and all(len(p.inserted) == 2 for p in doc.pages)
+    for pg, c in zip(pages, cap):
+        m, f, b = list(mrc.create_mrc_hocr_components(Image.fromarray(pg), [], denoise_mask='fast', bg_downsample=3))
+        assert np.array_equal(c['mask'], m) and np.array_equal(c['fg'], f) and np.array_equal(c['bg'], b)
