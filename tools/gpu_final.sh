@@ -8,4 +8,4 @@ timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 timeout 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/${T}_bench.json; tail -n 3 gpurun_out/${T}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err; echo "reference arm rc=$?"; cut -c1-400 gpurun_out/${T}_bench_reference.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches_64pages.csv python tools/profile_step.py --pages 64 --steps 2 --warmup 1 > gpurun_out/${T}_ncu_l.log 2>&1; echo "launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_noise|k_gray|k_sauvola_fused|k_mask|k_opt|k_resample" -s 10 -c 10 -o gpurun_out/${T}_full -f python tools/profile_step.py --pages 64 --warmup 1 --steps 1 > gpurun_out/${T}_ncu_f.log 2>&1; echo "full rc=$?"; tail -n 2 gpurun_out/${T}_ncu_f.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_noise|k_gray|k_sauvola_fused|k_mask|k_opt|k_resample}" -s ${NCU_SKIP:-10} -c ${NCU_COUNT:-10} -o gpurun_out/${T}_full -f python tools/profile_step.py --pages 64 --warmup 1 --steps 1 > gpurun_out/${T}_ncu_f.log 2>&1; echo "full rc=$?"; tail -n 2 gpurun_out/${T}_ncu_f.log
