@@ -36,9 +36,12 @@ __device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch
 }
 
 // One tile of one page.  256 threads as 32 x 8: no integer division in the loops.
-template <int RHI, int TH, int TW>
+// Conversions stay off the (quarter-rate) conversion unit: integer sums become doubles as 2^52 + x - 2^52 on the FP64 pipe,
+// and for radius <= 16 the vertical pass leaves its float32-rounded results in shared memory AS doubles (TMP = double:
+// exactly the same values), so the horizontal pass loads its operands ready to use.
+template <int RHI, int TH, int TW, typename TMP>
 __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t *in, uint8_t *out, int x0, int y0,
-                                          int radius, const double *sw, float *stmp, uint8_t *sg)
+                                          int radius, const double *sw, TMP *stmp, uint8_t *sg)
 {
     constexpr int GW = TW + 2 * RHI;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -55,10 +58,10 @@ __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t
     for (int ly = ty; ly < TH; ly += 8)
         for (int lx = tx; lx < gw; lx += 32) {
             const uint8_t *c = sg + (ly + radius) * GW + lx;
-            double acc = __dmul_rn((double)c[0], sw[0]);
+            double acc = __dmul_rn(u2d(c[0]), sw[0]);
             for (int j = radius; j >= 1; j--)
-                acc = __dadd_rn(acc, __dmul_rn((double)((int)c[-j * GW] + (int)c[j * GW]), sw[j]));
-            stmp[ly * GW + lx] = __double2float_rn(acc);
+                acc = __dadd_rn(acc, __dmul_rn(u2d((uint32_t)c[-j * GW] + (uint32_t)c[j * GW]), sw[j]));
+            stmp[ly * GW + lx] = (TMP)__double2float_rn(acc);            // float32 store between the axes (scipy)
         }
     __syncthreads();
     // axis 1 (horizontal) + uint8 truncation
@@ -68,7 +71,7 @@ __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t
         for (int lx = tx; lx < TW; lx += 32) {
             const int x = x0 + lx;
             if (x >= p.W) break;
-            const float *c = stmp + ly * GW + lx + radius;
+            const TMP *c = stmp + ly * GW + lx + radius;
             double acc = __dmul_rn((double)c[0], sw[0]);
             for (int j = radius; j >= 1; j--)
                 acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)c[-j], (double)c[j]), sw[j]));
@@ -77,6 +80,9 @@ __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t
         }
     }
 }
+
+template <int RHI> struct BlurTmp { using type = float; };      // radius up to 128: the tile's halo needs the shared memory
+template <> struct BlurTmp<16> { using type = double; };
 
 __device__ __forceinline__ int page_radius(const GrayBlurParams &p, int page, double &sigma)
 {
@@ -96,7 +102,8 @@ __global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double *sw = reinterpret_cast<double *>(smem_raw);                    // RHI+1 weights
     double *sphi = sw + (RHI + 1);                                        // 2*RHI+1 scratch
-    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));        // TH x GW
+    using TMP = typename BlurTmp<RHI>::type;
+    TMP *stmp = reinterpret_cast<TMP *>(sphi + (2 * RHI + 1));            // TH x GW
     uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);            // (TH + 2 RHI) x GW
 
     const int page = blockIdx.z;
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(256) k_gray_blur(const GrayBlurParams p)
         return;
     }
     blur_weights(radius, sigma, sw, sphi);
-    blur_tile<RHI, TH, TW>(p, in, out, x0, y0, radius, sw, stmp, sg);
+    blur_tile<RHI, TH, TW, TMP>(p, in, out, x0, y0, radius, sw, stmp, sg);
 }
 
 // Large-radius configuration (RLO..RHI): persistent CTAs walk the pages, skip those the small
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     double *sw = reinterpret_cast<double *>(smem_raw);
     double *sphi = sw + (RHI + 1);
-    float *stmp = reinterpret_cast<float *>(sphi + (2 * RHI + 1));
+    using TMP = typename BlurTmp<RHI>::type;
+    TMP *stmp = reinterpret_cast<TMP *>(sphi + (2 * RHI + 1));
     uint8_t *sg = reinterpret_cast<uint8_t *>(stmp + TH * GW);
     const int tiles_x = (p.W + TW - 1) / TW, tiles_y = (p.H + TH - 1) / TH;
     for (int page = 0; page < n_pages; page++) {
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p,
         uint8_t *out = p.out + (int64_t)page * p.out_stride;
         for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
             __syncthreads();
-            blur_tile<RHI, TH, TW>(p, in, out, (t % tiles_x) * TW, (t / tiles_x) * TH, radius, sw, stmp, sg);
+            blur_tile<RHI, TH, TW, TMP>(p, in, out, (t % tiles_x) * TW, (t / tiles_x) * TH, radius, sw, stmp, sg);
         }
     }
 }
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(256, MINB) k_gray_blur_fast(const GrayBlurPara
 template <int RHI, int TH, int TW>
 constexpr size_t gray_blur_smem()
 {
-    return sizeof(double) * (RHI + 1) + sizeof(double) * (2 * RHI + 1) + sizeof(float) * TH * (TW + 2 * RHI) +
+    return sizeof(double) * (RHI + 1) + sizeof(double) * (2 * RHI + 1) + sizeof(typename BlurTmp<RHI>::type) * TH * (TW + 2 * RHI) +
            (size_t)(TH + 2 * RHI) * (TW + 2 * RHI);
 }
 
