@@ -26,6 +26,7 @@ struct GrayBlurParams {
     int *err;                // device error flag (radius out of range), may be null
     int rlo;                 // tiled kernel: smallest radius it handles (5 when the fast kernel ran, else 0)
     int fast_rmin;           // fast kernel: smallest radius it handles (0; 3 behind the fused threshold kernel)
+    int vec4;                // planes, pitches and strides are 4-byte aligned: the tiled kernels load 4 pixels per thread
 };
 
 __device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch, int C, int y, int x)
@@ -39,28 +40,45 @@ __device__ __forceinline__ uint32_t load_gray(const uint8_t *page, int64_t pitch
 // Conversions stay off the (quarter-rate) conversion unit: integer sums become doubles as 2^52 + x - 2^52 on the FP64 pipe,
 // and for radius <= 16 the vertical pass leaves its float32-rounded results in shared memory AS doubles (TMP = double:
 // exactly the same values), so the horizontal pass loads its operands ready to use.
+template <int C>
+__device__ __forceinline__ uint32_t load_gray4(const GrayBlurParams &p, const uint8_t *in, int y, int x);
+
+// The gray tile (+ halo) is fetched as aligned groups of 4 pixels (3 words of RGB -> one word of gray, load_gray4; only
+// groups that touch the page edge take the per-pixel reflected form): the tile's rows in shared memory start at the
+// 4-aligned column xs <= x0 - radius, `off` columns before the first one the passes use.
 template <int RHI, int TH, int TW, typename TMP>
 __device__ __forceinline__ void blur_tile(const GrayBlurParams &p, const uint8_t *in, uint8_t *out, int x0, int y0,
                                           int radius, const double *sw, TMP *stmp, uint8_t *sg)
 {
-    constexpr int GW = TW + 2 * RHI;
+    constexpr int GW = TW + 2 * RHI, SGW = GW + 8;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gw = TW + 2 * radius, gh = TH + 2 * radius;
-    for (int ly = ty; ly < gh; ly += 8) {
-        const int y = reflect_idx(y0 - radius + ly, p.H);
-        for (int lx = tx; lx < gw; lx += 32) {
-            const int x = reflect_idx(x0 - radius + lx, p.W);
-            sg[ly * GW + lx] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+    const int gx0 = x0 - radius, xs = (gx0 >> 2) << 2, off = gx0 - xs;
+    if (p.vec4) {
+        const int ngrp = (off + gw + 3) >> 2;
+        for (int ly = ty; ly < gh; ly += 8) {
+            const int y = reflect_idx(y0 - radius + ly, p.H);
+            uint32_t *row = reinterpret_cast<uint32_t *>(sg + ly * SGW);
+            for (int g = tx; g < ngrp; g += 32)
+                row[g] = p.C == 3 ? load_gray4<3>(p, in, y, xs + 4 * g) : load_gray4<1>(p, in, y, xs + 4 * g);
+        }
+    } else {
+        for (int ly = ty; ly < gh; ly += 8) {
+            const int y = reflect_idx(y0 - radius + ly, p.H);
+            for (int lx = tx; lx < gw; lx += 32) {
+                const int x = reflect_idx(gx0 + lx, p.W);
+                sg[ly * SGW + off + lx] = (uint8_t)load_gray(in, p.in_pitch, p.C, y, x);
+            }
         }
     }
     __syncthreads();
     // axis 0 (vertical), for every column incl. the horizontal halo
     for (int ly = ty; ly < TH; ly += 8)
         for (int lx = tx; lx < gw; lx += 32) {
-            const uint8_t *c = sg + (ly + radius) * GW + lx;
+            const uint8_t *c = sg + (ly + radius) * SGW + off + lx;
             double acc = __dmul_rn(u2d(c[0]), sw[0]);
             for (int j = radius; j >= 1; j--)
-                acc = __dadd_rn(acc, __dmul_rn(u2d((uint32_t)c[-j * GW] + (uint32_t)c[j * GW]), sw[j]));
+                acc = __dadd_rn(acc, __dmul_rn(u2d((uint32_t)c[-j * SGW] + (uint32_t)c[j * SGW]), sw[j]));
             stmp[ly * GW + lx] = (TMP)__double2float_rn(acc);            // float32 store between the axes (scipy)
         }
     __syncthreads();
@@ -274,7 +292,7 @@ template <int RHI, int TH, int TW>
 constexpr size_t gray_blur_smem()
 {
     return sizeof(double) * (RHI + 1) + sizeof(double) * (2 * RHI + 1) + sizeof(typename BlurTmp<RHI>::type) * TH * (TW + 2 * RHI) +
-           (size_t)(TH + 2 * RHI) * (TW + 2 * RHI);
+           (size_t)(TH + 2 * RHI) * (TW + 2 * RHI + 8);
 }
 
 }  // namespace
@@ -283,10 +301,12 @@ int launch_gray_blur(const uint8_t *in, int64_t in_pitch, int64_t in_stride, int
                      uint8_t *out, int64_t out_pitch, int64_t out_stride,
                      int W, int H, int N, const double *sigma, int *err_flag, cudaStream_t st)
 {
-    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0, 0};
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 0, 0, 0};
     // fast marching kernel: needs 4-byte aligned rows and an image at least as large as its reflect reach
-    const bool fast_ok = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
-                         !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
+    const bool aligned4 = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
+                          !(in_stride & 3) && !(out_stride & 3);
+    const bool fast_ok = aligned4 && W >= 8 && H >= 8;
+    p.vec4 = aligned4 ? 1 : 0;
     if (fast_ok) {
         dim3 grid(cdiv(W, 120), cdiv(cdiv(H, FB_BAND), 8), N);
         // 6 CTAs / SM (40 registers, a few spills) beats 4 (60 registers) by 10 %
@@ -336,7 +356,7 @@ int launch_gray_blur_min_radius(const uint8_t *in, int64_t in_pitch, int64_t in_
 {
     if (!sigma) return B200MRC_OK;
     if (rmin != 3) return B200MRC_ERR_UNSUPPORTED;
-    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 5, rmin};
+    GrayBlurParams p{in, in_pitch, in_stride, C, out, out_pitch, out_stride, W, H, sigma, err_flag, 5, rmin, 1};   // vec4: fast_ok is required below
     const bool fast_ok = !(in_pitch & 3) && !(out_pitch & 3) && !((uintptr_t)in & 3) && !((uintptr_t)out & 3) &&
                          !(in_stride & 3) && !(out_stride & 3) && W >= 8 && H >= 8;
     if (!fast_ok) return B200MRC_ERR_ALIGNMENT;
