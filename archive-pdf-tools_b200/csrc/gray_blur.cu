@@ -172,6 +172,21 @@ __global__ void __launch_bounds__(256) k_gray_blur_large(const GrayBlurParams p,
         blur_weights(radius, sigma, sw, sphi);
         const uint8_t *in = p.in + (int64_t)page * p.in_stride;
         uint8_t *out = p.out + (int64_t)page * p.out_stride;
+        if constexpr (RHI > 32 && RLO <= 32) {
+            // radius <= 32 inside the wide-radius launch: a 32 x 64 tile with a 32-pixel halo budget fits the same shared
+            // memory and fetches 4.4x its pixels at radius 24, where the 16 x 32 tile sized for radius 128 fetches 10x
+            if (radius <= 32) {
+                constexpr int MTH = 32, MTW = 64, MR = 32;
+                float *mtmp = reinterpret_cast<float *>(stmp);
+                uint8_t *msg = reinterpret_cast<uint8_t *>(mtmp + MTH * (MTW + 2 * MR));
+                const int mx = (p.W + MTW - 1) / MTW, my = (p.H + MTH - 1) / MTH;
+                for (int t = blockIdx.x; t < mx * my; t += gridDim.x) {
+                    __syncthreads();
+                    blur_tile<MR, MTH, MTW, float>(p, in, out, (t % mx) * MTW, (t / mx) * MTH, radius, sw, mtmp, msg);
+                }
+                continue;
+            }
+        }
         for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
             __syncthreads();
             blur_tile<RHI, TH, TW, TMP>(p, in, out, (t % tiles_x) * TW, (t / tiles_x) * TH, radius, sw, stmp, sg);
