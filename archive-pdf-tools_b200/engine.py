@@ -390,7 +390,7 @@ class StreamedDecomposer:
     staging; the (un)pitching is a device-to-device b200mrc_copy2d on the compute stream.  Host tensors should be
     pinned."""
 
-    def __init__(self, eng, n_pages, h, w, c, chunk=4, bg_downsample=None, fg_downsample=None, mask_only=False,
+    def __init__(self, eng, n_pages, h, w, c, chunk=8, bg_downsample=None, fg_downsample=None, mask_only=False,
                  buffers=4, compute_streams=2, packed_mask=False, mask_transport='packed', unpack_workers=3):
         self.eng, self.n, self.h, self.w, self.c = eng, n_pages, h, w, c
         # mask_transport='packed' (default): the mask crosses the bus as mode-'1' rows (1 bit per pixel) and worker

@@ -434,7 +434,7 @@ def main():
         host = run.host
         del run.batch
         torch.cuda.empty_cache()
-        e2e_chunk = int(os.environ.get('B200MRC_E2E_CHUNK', '4' if H * W * C > 2e7 else ('8' if C == 3 else '16')))
+        e2e_chunk = int(os.environ.get('B200MRC_E2E_CHUNK', '4' if H * W * C > 5e7 else ('8' if C == 3 else '16')))   # 8 RGB pages of 3300x2550: profiles/r2r_e2e_sweep.txt
         e2e_streams = int(os.environ.get('B200MRC_E2E_STREAMS', '2'))
         e2e_buffers = int(os.environ.get('B200MRC_E2E_BUFFERS', '4'))
         last = 'mask' if cfg['mask_only'] else 'bg'
