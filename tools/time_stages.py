@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-stage timing of the staged pipeline (CUDA events), for quick A/B runs:
-    B200MRC_OPT_K=4 B200MRC_OPT_SW=224 python tools/time_stages.py --pages 64"""
+    B200MRC_IIRW_MODE=trio python tools/time_stages.py --pages 64      (tuning knobs: INTEGRATION.md section 6)"""
 import argparse, os, sys, json
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
