@@ -9,6 +9,8 @@ uint8 tensor [N, H, pitch] with pitch = round_up(W*C, 16) so rows are 16-byte al
 import ctypes as C
 import threading
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -65,9 +67,16 @@ class Plane:
         """host: uint8/bool ndarray or CPU tensor [N,H,W] / [N,H,W,C] (pinned for async copies)."""
         if not isinstance(host, torch.Tensor):
             host = np.ascontiguousarray(host).view(np.uint8)
-            if not host.flags.writeable:
-                host = host.copy()
-        ht = host if isinstance(host, torch.Tensor) else torch.from_numpy(host)
+        if isinstance(host, torch.Tensor):
+            ht = host
+        elif host.flags.writeable:
+            ht = torch.from_numpy(host)
+        else:
+            # np.asarray(PIL image) is a read-only view of a bytes object: it is only read here, so wrap it as it is
+            # instead of copying 25 MB per RGB page to make it writable (torch warns about read-only arrays)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                ht = torch.from_numpy(host)
         ht = ht.reshape(self.n, self.h, self.w * self.c)
         if self.pitch == self.w * self.c:
             self.t.copy_(ht, non_blocking=non_blocking)
